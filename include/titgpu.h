@@ -1,0 +1,108 @@
+/* titgpu — C ABI of the B200-native WCSPH particle step.
+ *
+ * The reference (Jhuighuy/TitSolver) has no plugin / FFI layer for this path:
+ * it is header-only C++ templates instantiated in
+ * /root/reference/source/titwcsph/wcsph.cpp. This C ABI sits *underneath* a
+ * C++ facade that keeps the reference's template surface (include/tit/...);
+ * each entry point names the reference interface it replaces.
+ *
+ * Conventions: opaque handle, `int` status (0 = ok), no exceptions cross the
+ * boundary, one host thread per context, one context per GPU. All particle
+ * arrays are host pointers in the reference's particle order (fluid particles
+ * first, then fixed ones; /root/reference/source/tit/sph/particle_array.hpp:
+ * 188-199, 233-239). `stride_bytes` is the distance between consecutive
+ * particles' values (0 = packed), so that the reference's padded 32-byte
+ * Vec<double,3> arrays can be passed directly.
+ *
+ * There is no CPU fallback: every call fails with a CUDA error if no device
+ * is present.
+ */
+#ifndef TITGPU_H
+#define TITGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TITGPU_API __attribute__((visibility("default")))
+#else
+#define TITGPU_API
+#endif
+
+typedef struct titgpu_ctx titgpu_ctx;
+
+/* Smoothing kernels (/root/reference/source/tit/sph/kernel.hpp:428-454). */
+enum { TITGPU_KERNEL_CUBIC_SPLINE = 0, TITGPU_KERNEL_QUARTIC_SPLINE = 1, TITGPU_KERNEL_QUINTIC_SPLINE = 2,
+       TITGPU_KERNEL_QUARTIC_WENDLAND = 3, TITGPU_KERNEL_SIXTH_ORDER_WENDLAND = 4, TITGPU_KERNEL_EIGHTH_ORDER_WENDLAND = 5 };
+/* Equations of state (sph/equation_of_state.hpp:19-122). */
+enum { TITGPU_EOS_TAIT = 0, TITGPU_EOS_LINEAR_TAIT = 1 };
+/* Time integrators (sph/time_integrator.hpp:32-228). */
+enum { TITGPU_SYMPLECTIC_EULER = 0, TITGPU_VELOCITY_VERLET = 1, TITGPU_SSPRK2 = 2, TITGPU_SSPRK3 = 3 };
+
+/* Replaces the construction of FluidEquations / integrator / ParticleArray
+ * (wcsph.cpp:79-101): dimension (Space<Real,Dim>), kernel type, EOS type and
+ * integrator type are the template arguments of the reference. */
+TITGPU_API int titgpu_create(titgpu_ctx** ctx, int device, int dim, int kernel_id, int eos_id, int integrator_id);
+TITGPU_API int titgpu_destroy(titgpu_ctx* ctx);
+TITGPU_API const char* titgpu_last_error(const titgpu_ctx* ctx);
+
+/* FluidEquations{g, mu, ..., TaitEquationOfState{cs0, rho0, xi}, Kernel{}} and
+ * the uniform field h (fluid_equations.hpp:61-69, wcsph.cpp:116). The cell
+ * hints of GridSearch{h}/GridFaceSearch{h} (wcsph.cpp:145-150) are accepted
+ * for interface parity; the GPU hash always uses cells of one support radius
+ * (neighbour sets do not depend on the cell size). */
+TITGPU_API int titgpu_set_params(titgpu_ctx* ctx, double g, double mu, double cs0, double rho0, double xi, double h,
+                      double search_cell_hint, double face_cell_hint);
+
+/* The `Domain` (boundary-integral surface, normals into the fluid) and the
+ * `Containment` surface (winding number +1 inside) of FluidEquations
+ * (fluid_equations.hpp:528-529; wcsph.cpp:55-77). Vertex k of the domain
+ * surface is fixed particle k (wcsph.cpp:110-113). Faces hold `dim` vertex
+ * indices each. */
+TITGPU_API int titgpu_set_surface(titgpu_ctx* ctx, const double* verts, size_t nv, const uint64_t* faces, size_t nf,
+                       const double* inside_verts, size_t niv, const uint64_t* inside_faces, size_t nif);
+
+/* ParticleArray::append + field assignment (particle_array.hpp:188-199,
+ * 248-261). `field` is a reference field name: "r", "v", "rho", "m" are
+ * state; "dv_dt" seeds the force time-step limit. A change of
+ * (n_fluid, n_fixed) resets the particle set. */
+TITGPU_API int titgpu_upload(titgpu_ctx* ctx, size_t n_fluid, size_t n_fixed, const char* field, const void* host, size_t stride_bytes);
+
+/* field[particles] read-back (particle_array.hpp:264-276), any of the 17
+ * varying fields of fluid_equations.hpp:41-48, original particle order. */
+TITGPU_API int titgpu_download(titgpu_ctx* ctx, const char* field, void* host, size_t stride_bytes);
+
+/* FluidEquations::initialize (fluid_equations.hpp:79-89). */
+TITGPU_API int titgpu_initialize(titgpu_ctx* ctx);
+/* FluidEquations::prepare (fluid_equations.hpp:99-105). */
+TITGPU_API int titgpu_prepare(titgpu_ctx* ctx);
+/* prepare + compute_continuity + compute_momentum (fluid_equations.hpp:232-305)
+ * without advancing the state — for one-evaluation parity checks. */
+TITGPU_API int titgpu_rhs_only(titgpu_ctx* ctx);
+/* `nsteps` calls of <Integrator>::step(mesh, particles)
+ * (time_integrator.hpp:49, 98, 161). Returns the last dt. The derived output
+ * fields reflect the last step. */
+TITGPU_API int titgpu_step(titgpu_ctx* ctx, int nsteps, double* dt_last);
+
+/* ParticleMesh adjacency (particle_mesh.hpp:67-72, 137-147): CSR, rows in
+ * original particle order, columns ascending, self included. Call with
+ * cols == NULL to obtain nnz. */
+TITGPU_API int titgpu_neighbors(titgpu_ctx* ctx, uint64_t* row_offsets, uint64_t* cols, size_t cap, size_t* nnz);
+
+/* Block until all queued work of the context has finished. */
+TITGPU_API int titgpu_synchronize(titgpu_ctx* ctx);
+/* Number of CUDA kernels this context has launched so far. */
+TITGPU_API unsigned long long titgpu_launch_count(const titgpu_ctx* ctx);
+/* The CUDA stream the context launches on (cudaStream_t), for event timing. */
+TITGPU_API void* titgpu_stream(titgpu_ctx* ctx);
+/* Library version string. */
+TITGPU_API const char* titgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TITGPU_H */

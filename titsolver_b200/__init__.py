@@ -1,0 +1,192 @@
+"""titsolver_b200 — B200-native WCSPH particle step behind the TitSolver API.
+
+The product is `libtitgpu.so` (hand-written sm_100a CUDA kernels + a C ABI,
+see include/titgpu.h) and the C++ facade in include/tit/. This module is the
+thin ctypes binding used by the tests and bench.py; it mirrors the call
+sequence of /root/reference/source/titwcsph/wcsph.cpp.
+
+There is no CPU fallback: importing works without a GPU (so that the ABI can be
+inspected), every compute call requires one and raises `TitGpuError` otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import cases  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtitgpu.so")
+
+FIELDS = {
+    "m": 0, "gamma": 0, "rho": 0, "drho_dt": 0, "p": 0, "cs": 0, "phi": 0, "rho_raw": 0,
+    "grad_gamma": 1, "grad_rho": 1, "v": 1, "dv_dt": 1, "r": 1, "dr": 1, "N": 1,
+    "grad_v": 2, "L": 2,
+}
+
+ABI_SYMBOLS = [
+    "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
+    "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
+    "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
+]
+
+
+class TitGpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libtitgpu.so; fails loudly when the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TitGpuError(f"{LIB_PATH} is missing: build it with `python -m titsolver_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    d, vp, sz = C.c_double, C.c_void_p, C.c_size_t
+    u64p = C.POINTER(C.c_uint64)
+    lib.titgpu_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.titgpu_destroy.argtypes = [vp]
+    lib.titgpu_last_error.argtypes = [vp]
+    lib.titgpu_last_error.restype = C.c_char_p
+    lib.titgpu_set_params.argtypes = [vp] + [d] * 8
+    lib.titgpu_set_surface.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz]
+    lib.titgpu_upload.argtypes = [vp, sz, sz, C.c_char_p, vp, sz]
+    lib.titgpu_download.argtypes = [vp, C.c_char_p, vp, sz]
+    for f in ("titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_synchronize"):
+        getattr(lib, f).argtypes = [vp]
+    lib.titgpu_step.argtypes = [vp, C.c_int, C.POINTER(d)]
+    lib.titgpu_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
+    lib.titgpu_launch_count.argtypes = [vp]
+    lib.titgpu_launch_count.restype = C.c_ulonglong
+    lib.titgpu_stream.argtypes = [vp]
+    lib.titgpu_stream.restype = vp
+    lib.titgpu_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _arr(x, dtype=np.float64):
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype))
+
+
+class Solver:
+    """One GPU context == FluidEquations + integrator + ParticleArray + ParticleMesh
+    of the reference driver (wcsph.cpp:79-154)."""
+
+    def __init__(self, dim, kernel_id=4, eos_id=0, integrator_id=3, device=0):
+        self.lib = load_library()
+        self.dim = dim
+        self.h = C.c_void_p()
+        rc = self.lib.titgpu_create(C.byref(self.h), device, dim, kernel_id, eos_id, integrator_id)
+        if rc:
+            msg = self._err()
+            if self.h:
+                self.lib.titgpu_destroy(self.h)
+                self.h = C.c_void_p()
+            raise TitGpuError(f"titgpu_create failed: {msg}")
+        self.n_fluid = self.n_fixed = 0
+
+    @property
+    def n(self):
+        return self.n_fluid + self.n_fixed
+
+    def _err(self):
+        return (self.lib.titgpu_last_error(self.h) or b"").decode() if self.h else "no context"
+
+    def _ck(self, rc, what):
+        if rc:
+            raise TitGpuError(f"{what} failed: {self._err()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.titgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, g, mu, cs0, rho0, xi, h, search_hint=0.0, face_hint=0.0):
+        self._ck(self.lib.titgpu_set_params(self.h, g, mu, cs0, rho0, xi, h, search_hint, face_hint), "titgpu_set_params")
+
+    def set_surface(self, verts, faces, cverts, cfaces):
+        v, f, cv, cf = _arr(verts), _arr(faces, np.uint64), _arr(cverts), _arr(cfaces, np.uint64)
+        self._ck(self.lib.titgpu_set_surface(self.h, v.ctypes.data, len(v), f.ctypes.data, len(f), cv.ctypes.data, len(cv), cf.ctypes.data, len(cf)), "titgpu_set_surface")
+
+    def set_particles(self, n_fluid, n_fixed):
+        self.n_fluid, self.n_fixed = int(n_fluid), int(n_fixed)
+
+    def _shape(self, field):
+        k = FIELDS[field]
+        return (self.n,) if k == 0 else (self.n, self.dim) if k == 1 else (self.n, self.dim, self.dim)
+
+    def upload(self, field, a, stride_bytes=0):
+        a = _arr(a)
+        if stride_bytes == 0:
+            assert a.shape == self._shape(field), (field, a.shape, self._shape(field))
+        self._ck(self.lib.titgpu_upload(self.h, self.n_fluid, self.n_fixed, field.encode(), a.ctypes.data, stride_bytes), f"titgpu_upload({field})")
+
+    def upload_raw(self, field, ptr, stride_bytes=0):
+        """Upload from a raw host address (e.g. pinned memory)."""
+        self._ck(self.lib.titgpu_upload(self.h, self.n_fluid, self.n_fixed, field.encode(), ptr, stride_bytes), f"titgpu_upload({field})")
+
+    def download(self, field, out=None):
+        if out is None:
+            out = np.empty(self._shape(field))
+        self._ck(self.lib.titgpu_download(self.h, field.encode(), out.ctypes.data, 0), f"titgpu_download({field})")
+        return out
+
+    def download_raw(self, field, ptr, stride_bytes=0):
+        self._ck(self.lib.titgpu_download(self.h, field.encode(), ptr, stride_bytes), f"titgpu_download({field})")
+
+    def initialize(self):
+        self._ck(self.lib.titgpu_initialize(self.h), "titgpu_initialize")
+
+    def prepare(self):
+        self._ck(self.lib.titgpu_prepare(self.h), "titgpu_prepare")
+
+    def rhs_only(self):
+        self._ck(self.lib.titgpu_rhs_only(self.h), "titgpu_rhs_only")
+
+    def step(self, nsteps=1):
+        dt = C.c_double(0)
+        self._ck(self.lib.titgpu_step(self.h, nsteps, C.byref(dt)), "titgpu_step")
+        return dt.value
+
+    def neighbors(self):
+        nnz = C.c_size_t(0)
+        self._ck(self.lib.titgpu_neighbors(self.h, None, None, 0, C.byref(nnz)), "titgpu_neighbors")
+        off = np.zeros(self.n + 1, np.uint64)
+        cols = np.zeros(max(nnz.value, 1), np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        self._ck(self.lib.titgpu_neighbors(self.h, off.ctypes.data_as(u64p), cols.ctypes.data_as(u64p), nnz.value, C.byref(nnz)), "titgpu_neighbors")
+        return off, cols[: nnz.value]
+
+    def synchronize(self):
+        self._ck(self.lib.titgpu_synchronize(self.h), "titgpu_synchronize")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.titgpu_launch_count(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.titgpu_stream(self.h)
+
+
+def load_case(solver, case):
+    """Feed a `cases.Case` into a solver, in the order of wcsph.cpp:79-154."""
+    solver.set_params(case.g, case.mu, case.cs0, case.rho0, case.xi, case.h)
+    solver.set_surface(case.verts, case.faces, case.cverts, case.cfaces)
+    solver.set_particles(case.n_fluid, case.n_fixed)
+    solver.upload("r", case.r)
+    solver.upload("m", case.m)
+    solver.upload("rho", case.rho)

@@ -1,0 +1,135 @@
+// Host-side context of the B200 WCSPH engine (one context per GPU, one host
+// thread per context). Owns every device buffer; the templated engine
+// (engine.cuh) only launches kernels on them.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace titgpu {
+
+// Field ids, in the reference's varying-field order
+// (/root/reference/source/tit/sph/fluid_equations.hpp:41-48).
+enum FieldId : int {
+  F_m, F_gamma, F_grad_gamma, F_rho, F_drho_dt, F_grad_rho, F_p, F_cs, F_v, F_dv_dt, F_grad_v, F_r, F_dr, F_L, F_N, F_phi, F_rho_raw, F_COUNT
+};
+// 0 scalar, 1 vector, 2 matrix.
+constexpr int kFieldRank[F_COUNT] = {0, 0, 1, 0, 0, 1, 0, 0, 1, 1, 2, 1, 1, 2, 1, 0, 0};
+constexpr const char* kFieldName[F_COUNT] = {"m", "gamma", "grad_gamma", "rho", "drho_dt", "grad_rho", "p", "cs", "v", "dv_dt", "grad_v", "r", "dr", "L", "N", "phi", "rho_raw"};
+
+inline int field_width(int f, int dim) { return kFieldRank[f] == 0 ? 1 : kFieldRank[f] == 1 ? dim : dim * dim; }
+inline int field_by_name(const char* s) {
+  for (int f = 0; f < F_COUNT; ++f)
+    if (std::string(s) == kFieldName[f]) return f;
+  return -1;
+}
+
+struct DBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t b) {
+    if (b <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e == cudaSuccess) bytes = b;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template<class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Sorted-order particle state; two copies (ping-pong for the cell reorder and
+// for the fused RHS + update pass).
+struct StateBufs {
+  DBuf r, v, rho, m, r0, v0, rho0, orig;
+};
+
+struct EngineVTable;
+
+struct Ctx {
+  int device = 0, dim = 2, kernel_id = 4, eos_id = 0, integrator_id = 3;
+  cudaStream_t stream = nullptr;
+  const EngineVTable* vt = nullptr;
+  Params prm{};
+  bool params_set = false, surface_set = false, sized = false, grid_ready = false, initialized = false;
+  bool sorted_identity = true;  // state order == original order
+  size_t nf = 0, nx = 0, n = 0;
+  double search_hint = 0, face_hint = 0;
+
+  StateBufs st[2];
+  int cur = 0;  // st[cur] holds r/v/rho/...; individual fields may be swapped, see ptrs below
+  // Current pointers (fields swap independently).
+  double *r = nullptr, *v = nullptr, *rho = nullptr, *m = nullptr, *r0 = nullptr, *v0 = nullptr, *rho0 = nullptr;
+  int* orig = nullptr;
+  double *r_alt = nullptr, *v_alt = nullptr, *rho_alt = nullptr, *m_alt = nullptr, *r0_alt = nullptr, *v0_alt = nullptr, *rho0_alt = nullptr;
+  int* orig_alt = nullptr;
+
+  // Per-sorted-particle derived data.
+  DBuf cs, pq, pp;               // sound speed, p / rho^2, p
+  DBuf gamma_s, N_s, phi_s, phi2_s, dr_s, gv_s, gr_s, r_pre;  // post-integration scratch
+
+  // Hash / sort scratch.
+  DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp;
+
+  // Static boundary.
+  DBuf frames, fcell_start, fcell_faces, face_cells;
+  size_t nfaces = 0;
+  DBuf cverts, cfaces;
+  size_t ncfaces = 0;
+  DBuf gamma_fixed, gg_fixed;  // static gamma / grad gamma of the fixed particles
+  DBuf rho_fx, p_fx;           // wall density / pressure by fixed id
+  bool fixed_cache_valid = false;
+
+  // Outputs, original particle order, one buffer per field.
+  DBuf out[F_COUNT];
+  DBuf staging;
+
+  // Device scalars: [0] dt, [1] max |dv_dt|^2 of the last RHS (bits), [2] dt
+  // reduction (bits), [3] spare.
+  DBuf scalars;
+
+  // Host copies of the surfaces.
+  std::vector<double> h_verts, h_cverts;
+  std::vector<uint64_t> h_faces, h_cfaces;
+
+  // Counters.
+  unsigned long long launches = 0;
+
+  std::string err;
+};
+
+// Per-(dim, kernel) entry points, filled by the explicit instantiations.
+struct EngineVTable {
+  void (*fill_params)(Ctx&);
+  int (*seed_fmax)(Ctx&);
+  int (*set_surface)(Ctx&);
+  int (*initialize)(Ctx&);
+  int (*prepare)(Ctx&, bool write_out);
+  int (*rhs_only)(Ctx&);
+  int (*step)(Ctx&, int nsteps);
+  int (*neighbors)(Ctx&, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz);
+  int (*download_state)(Ctx&, int field, double* dst_dev);  // unsort into original order
+  int (*upload_state)(Ctx&, int field, const double* src_dev);
+};
+
+const EngineVTable* get_engine(int dim, int kernel_id);
+void register_engine(int dim, int kernel_id, const EngineVTable* vt);
+
+#define TIT_CUDA_OK(ctx, expr)                                                                     \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      (ctx).err = std::string(#expr) + ": " + cudaGetErrorString(e_);                              \
+      return 1;                                                                                    \
+    }                                                                                              \
+  } while (0)
+
+}  // namespace titgpu

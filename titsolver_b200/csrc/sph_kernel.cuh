@@ -1,0 +1,223 @@
+// Device-side smoothing kernel: value, gradient coefficient and the
+// semi-analytical wall integrals (flux of W and of its antigradient over a
+// boundary segment / triangle clipped by the support sphere).
+//
+// Replaces, for the GPU path,
+//   /root/reference/source/tit/sph/kernel.hpp:142-163  operator(), grad
+//   /root/reference/source/tit/sph/kernel.hpp:194-221  flux, antigrad_flux
+//   /root/reference/source/tit/sph/kernel.hpp:287-399  unit_segment_integral,
+//                                                      unit_triangle_integral
+// using the per-kernel recurrences in kernels_gen.cuh (tools/gen_kernels.py).
+//
+// Boundary faces never move, so their local frames (normal, in-plane axes,
+// projected vertices) are precomputed once per surface (FaceFrame) instead of
+// being re-derived from the vertices on every evaluation as the reference does.
+#pragma once
+
+#include "common.cuh"
+#include "kernels_gen.cuh"
+
+namespace titgpu {
+
+template<int D> struct FaceFrame;
+// 2-D segment: a, unit normal n = normalize((ba.y, -ba.x)), unit tangent e, length.
+template<> struct FaceFrame<2> {
+  double a[2], n[2], e[2], len;
+  double ctr[2];        // mean of the vertices (r_s of the face)
+  double lo[2], hi[2];  // bbox
+  unsigned v[2];        // vertex (== fixed particle) indices
+};
+// 3-D triangle: a, e1 = normalize(ba), n = normalize(cross(ba, ca)),
+// e2 = normalize(cross(n_w, e1)); b and c in (e1, e2) coordinates relative to a.
+template<> struct FaceFrame<3> {
+  double a[3], n[3], e1[3], e2[3];
+  double bx, cx, cy;
+  double ctr[3];
+  double lo[3], hi[3];
+  unsigned v[3];
+};
+
+template<int KID>
+struct SphKernel {
+  using KG = titgpu_gen::KernelGen<KID>;
+
+  template<int D> TIT_HD static constexpr double weight() { return D == 1 ? KG::weight1 : D == 2 ? KG::weight2 : KG::weight3; }
+
+  // W(x) given r = |x| (kernel.hpp:142-151).
+  TIT_HD static double value(const Params& P, double rn) { return P.w_val * KG::unit_value(P.hinv * rn); }
+
+  // grad W = c * x with c = w h^-1 w'(q) / |x|; zero for |x| < tiny
+  // (normalize(), core/_vec/vec.hpp:663-678).
+  TIT_HD static double grad_coef(const Params& P, double d2, double rn) {
+    if (d2 < P.tiny2) return 0.0;
+    return P.w_val * P.hinv * KG::unit_deriv(P.hinv * rn) / rn;
+  }
+
+  // ---- 2-D: clipped segment integral (kernel.hpp:287-314) ----
+  template<bool Anti, int I>
+  TIT_HD static double seg_prim(double eta, double z, bool eta_tiny) {
+    const double rho = sqrt(fma(z, z, eta * eta));
+    const double A = atan2(z, eta);
+    const double L = eta_tiny ? 0.0 : copysign(log1p((fabs(z) + z * z / (rho + eta)) / eta), z);
+    if constexpr (Anti) return KG::template seg_antigrad<I>(eta, z, rho, A, L);
+    else return KG::template seg_flux<I>(eta, z, rho, A, L);
+  }
+  template<bool Anti, int I>
+  TIT_HD static double seg_piece(const Params& P, double eta, double z_min, double z_max) {
+    const double c = KG::cutoff(I);
+    if (eta >= c) return 0.0;
+    const double z_clip = sqrt(c * c - eta * eta);
+    const double z_lo = fmax(z_min, -z_clip);
+    const double z_hi = fmin(z_max, +z_clip);
+    if (z_lo >= z_hi) return 0.0;
+    const bool et = fabs(eta) <= P.tiny;
+    return seg_prim<Anti, I>(eta, z_hi, et) - seg_prim<Anti, I>(eta, z_lo, et);
+  }
+  template<bool Anti, int I = 0>
+  TIT_HD static double seg_integral(const Params& P, double eta, double z_min, double z_max) {
+    if constexpr (I >= KG::num_pieces) return 0.0;
+    else return seg_piece<Anti, I>(P, eta, z_min, z_max) + seg_integral<Anti, I + 1>(P, eta, z_min, z_max);
+  }
+
+  // ---- 3-D: clipped triangle integral (kernel.hpp:319-399) ----
+  template<bool Anti, int I>
+  TIT_HD static double line_prim(const Params& P, double eta, double delta, double delta_sqr, double beta_sqr, double beta, double z) {
+    const double rho = sqrt(fma(z, z, beta_sqr));
+    const double A = fabs(delta) <= P.tiny ? 0.0 : atan2(delta * z * (rho - eta), fma(delta_sqr, rho, z * z * eta));
+    const double L = fabs(beta) <= P.tiny ? 0.0 : copysign(log1p((fabs(z) + z * z / (rho + beta)) / beta), z);
+    if constexpr (Anti) return KG::template tri_antigrad_line<I>(eta, delta, z, rho, A, L);
+    else return KG::template tri_flux_line<I>(eta, delta, z, rho, A, L);
+  }
+  template<bool Anti, int I>
+  TIT_HD static double tri_edge(const Params& P, double eta, double radius_sqr, double sector, const double* p0, const double* p1) {
+    const double ex = p1[0] - p0[0], ey = p1[1] - p0[1];
+    const double len2 = ex * ex + ey * ey;
+    if (len2 <= P.tiny2) return 0.0;
+    const double len = sqrt(len2);
+    const double tx = ex / len, ty = ey / len;
+    const double delta = p0[0] * ty - p0[1] * tx;  // det(p0, tangent)
+    const double delta_sqr = delta * delta;
+    const double beta_sqr = eta * eta + delta_sqr;
+    const double beta = sqrt(beta_sqr);
+    const double z_start = p0[0] * tx + p0[1] * ty;
+    const double z_finish = z_start + len;
+    double zs[4];
+    int nz = 0;
+    zs[nz++] = z_start;
+    if (radius_sqr > delta_sqr) {
+      const double z_clip = sqrt(radius_sqr - delta_sqr);
+      if (z_start < -z_clip && -z_clip < z_finish) zs[nz++] = -z_clip;
+      if (z_start < +z_clip && +z_clip < z_finish) zs[nz++] = +z_clip;
+    }
+    zs[nz++] = z_finish;
+    double result = 0.0;
+    for (int i = 0; i + 1 < nz; ++i) {
+      const double z_lo = zs[i], z_hi = zs[i + 1];
+      if (fabs(z_hi - z_lo) <= P.tiny) continue;
+      const double zm = 0.5 * (z_lo + z_hi);
+      if (zm * zm + delta_sqr < radius_sqr) {
+        result += line_prim<Anti, I>(P, eta, delta, delta_sqr, beta_sqr, beta, z_hi) - line_prim<Anti, I>(P, eta, delta, delta_sqr, beta_sqr, beta, z_lo);
+      } else {
+        result += sector * atan2(delta * (z_hi - z_lo), fma(z_lo, z_hi, delta_sqr));
+      }
+    }
+    return result;
+  }
+  template<bool Anti, int I>
+  TIT_HD static double tri_piece(const Params& P, double eta, const double* a, const double* b, const double* c) {
+    const double cut = KG::cutoff(I);
+    if (eta >= cut) return 0.0;
+    const double radius_sqr = cut * cut - eta * eta;
+    double sector;
+    if constexpr (Anti) sector = KG::template tri_antigrad_sector<I>(eta);
+    else sector = KG::template tri_flux_sector<I>(eta);
+    return tri_edge<Anti, I>(P, eta, radius_sqr, sector, a, b) + tri_edge<Anti, I>(P, eta, radius_sqr, sector, b, c) + tri_edge<Anti, I>(P, eta, radius_sqr, sector, c, a);
+  }
+  template<bool Anti, int I = 0>
+  TIT_HD static double tri_integral(const Params& P, double eta, const double* a, const double* b, const double* c) {
+    if constexpr (I >= KG::num_pieces) return 0.0;
+    else return tri_piece<Anti, I>(P, eta, a, b, c) + tri_integral<Anti, I + 1>(P, eta, a, b, c);
+  }
+
+  // Scalar flux magnitude along the face normal: grad gamma_as = n * flux_n
+  // (kernel.hpp:194-206). `Anti` selects the antigradient flux (:209-221), which
+  // carries the sign of the wall distance.
+  template<bool Anti>
+  TIT_HD static double face_integral(const Params& P, const FaceFrame<2>& f, const Vec<2>& x) {
+    const double ax = f.a[0] - x[0], ay = f.a[1] - x[1];
+    const double d = -(ax * f.n[0] + ay * f.n[1]) * P.hinv;
+    const double z_min = (ax * f.e[0] + ay * f.e[1]) * P.hinv;
+    const double z_max = z_min + f.len * P.hinv;
+    const double u = seg_integral<Anti>(P, fabs(d), z_min, z_max);
+    if constexpr (Anti) return copysign(P.w_anti, d) * u;
+    else return P.w_flux * u;
+  }
+  template<bool Anti>
+  TIT_HD static double face_integral(const Params& P, const FaceFrame<3>& f, const Vec<3>& x) {
+    const double ax = f.a[0] - x[0], ay = f.a[1] - x[1], az = f.a[2] - x[2];
+    const double d = -(ax * f.n[0] + ay * f.n[1] + az * f.n[2]) * P.hinv;
+    double pa[2], pb[2], pc[2];
+    pa[0] = (ax * f.e1[0] + ay * f.e1[1] + az * f.e1[2]) * P.hinv;
+    pa[1] = (ax * f.e2[0] + ay * f.e2[1] + az * f.e2[2]) * P.hinv;
+    pb[0] = pa[0] + f.bx * P.hinv;
+    pb[1] = pa[1];
+    pc[0] = pa[0] + f.cx * P.hinv;
+    pc[1] = pa[1] + f.cy * P.hinv;
+    const double u = tri_integral<Anti>(P, fabs(d), pa, pb, pc);
+    if constexpr (Anti) return copysign(P.w_anti, d) * u;
+    else return P.w_flux * u;
+  }
+};
+
+// Exact sphere/face intersection test of the reference face search
+// (geom/segment.hpp:92-112, geom/triangle.hpp:116-186): bbox overlap, then
+// closest point on the face within the radius.
+TIT_HD bool face_intersects(const FaceFrame<2>& f, const Vec<2>& c, double radius, double radius2, double tiny) {
+  for (int d = 0; d < 2; ++d)
+    if (!(c[d] - radius <= f.hi[d] && f.lo[d] <= c[d] + radius)) return false;
+  // clamp(): a + t * ba with t in [0, 1]; ba = e * len.
+  const double px = c[0] - f.a[0], py = c[1] - f.a[1];
+  const double len2 = f.len * f.len;
+  double qx, qy;
+  if (fabs(len2) <= tiny) {
+    qx = f.a[0]; qy = f.a[1];
+  } else {
+    const double bax = f.e[0] * f.len, bay = f.e[1] * f.len;
+    const double t = (px * bax + py * bay) / len2;
+    if (t < 0.0) { qx = f.a[0]; qy = f.a[1]; }
+    else if (t > 1.0) { qx = f.a[0] + bax; qy = f.a[1] + bay; }
+    else { qx = f.a[0] + t * bax; qy = f.a[1] + t * bay; }
+  }
+  const double dx = qx - c[0], dy = qy - c[1];
+  return dx * dx + dy * dy <= radius2;
+}
+
+TIT_HD bool face_intersects(const FaceFrame<3>& f, const Vec<3>& p, double radius, double radius2, double tiny) {
+  for (int d = 0; d < 3; ++d)
+    if (!(p[d] - radius <= f.hi[d] && f.lo[d] <= p[d] + radius)) return false;
+  // Work in the triangle frame: a = (0,0), b = (bx,0), c = (cx,cy), point
+  // (u, v, w) with w the plane distance. Closest point on the triangle follows
+  // the region walk of geom/triangle.hpp:137-181 (Ericson), evaluated in-plane.
+  const double x = p[0] - f.a[0], y = p[1] - f.a[1], z = p[2] - f.a[2];
+  const double u = x * f.e1[0] + y * f.e1[1] + z * f.e1[2];
+  const double v = x * f.e2[0] + y * f.e2[1] + z * f.e2[2];
+  const double w = x * f.n[0] + y * f.n[1] + z * f.n[2];
+  const double bx = f.bx, cx = f.cx, cy = f.cy;
+  (void)tiny;
+  double qu, qv;
+  const double d1 = bx * u, d2 = cx * u + cy * v;
+  const double d3 = bx * (u - bx), d4 = cx * (u - bx) + cy * v;
+  const double d5 = bx * (u - cx), d6 = cx * (u - cx) + cy * (v - cy);
+  const double vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+  if (d1 <= 0.0 && d2 <= 0.0) { qu = 0; qv = 0; }
+  else if (d3 >= 0.0 && d4 <= d3) { qu = bx; qv = 0; }
+  else if (d6 >= 0.0 && d5 <= d6) { qu = cx; qv = cy; }
+  else if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) { const double t = d1 / (d1 - d3); qu = t * bx; qv = 0; }
+  else if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { const double t = d2 / (d2 - d6); qu = t * cx; qv = t * cy; }
+  else if (va <= 0.0 && d4 >= d3 && d5 >= d6) { const double t = (d4 - d3) / ((d4 - d3) + (d5 - d6)); qu = bx + t * (cx - bx); qv = t * cy; }
+  else { const double s = 1.0 / (va + vb + vc); const double tv = vb * s, tw = vc * s; qu = tv * bx + tw * cx; qv = tw * cy; }
+  const double du = qu - u, dv = qv - v;
+  return du * du + dv * dv + w * w <= radius2;
+}
+
+}  // namespace titgpu

@@ -1,0 +1,316 @@
+// extern "C" boundary of libtitgpu.so (see include/titgpu.h). Plain pointers
+// and sizes only; dispatches to the (dimension, kernel) engine instantiation.
+#include "../../include/titgpu.h"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "context.h"
+
+struct titgpu_ctx {
+  titgpu::Ctx c;
+};
+
+namespace titgpu {
+
+namespace {
+const EngineVTable* g_engines[4][6] = {};
+}
+void register_engine(int dim, int kernel_id, const EngineVTable* vt) {
+  if (dim >= 2 && dim <= 3 && kernel_id >= 0 && kernel_id < 6) g_engines[dim][kernel_id] = vt;
+}
+const EngineVTable* get_engine(int dim, int kernel_id) {
+  if (dim < 2 || dim > 3 || kernel_id < 0 || kernel_id >= 6) return nullptr;
+  return g_engines[dim][kernel_id];
+}
+
+namespace {
+
+int fail(Ctx& c, const std::string& msg) {
+  c.err = msg;
+  return 1;
+}
+
+int alloc_particles(Ctx& c) {
+  const size_t n = std::max<size_t>(c.n, 1), D = size_t(c.dim);
+  auto pair = [&](DBuf& a, DBuf& b, size_t bytes) -> cudaError_t {
+    cudaError_t e = a.ensure(bytes);
+    if (e != cudaSuccess) return e;
+    return b.ensure(bytes);
+  };
+  StateBufs &A = c.st[0], &B = c.st[1];
+  TIT_CUDA_OK(c, pair(A.r, B.r, n * D * 8));
+  TIT_CUDA_OK(c, pair(A.v, B.v, n * D * 8));
+  TIT_CUDA_OK(c, pair(A.rho, B.rho, n * 8));
+  TIT_CUDA_OK(c, pair(A.m, B.m, n * 8));
+  TIT_CUDA_OK(c, pair(A.r0, B.r0, n * D * 8));
+  TIT_CUDA_OK(c, pair(A.v0, B.v0, n * D * 8));
+  TIT_CUDA_OK(c, pair(A.rho0, B.rho0, n * 8));
+  TIT_CUDA_OK(c, pair(A.orig, B.orig, n * 4));
+  c.r = A.r.as<double>(); c.r_alt = B.r.as<double>();
+  c.v = A.v.as<double>(); c.v_alt = B.v.as<double>();
+  c.rho = A.rho.as<double>(); c.rho_alt = B.rho.as<double>();
+  c.m = A.m.as<double>(); c.m_alt = B.m.as<double>();
+  c.r0 = A.r0.as<double>(); c.r0_alt = B.r0.as<double>();
+  c.v0 = A.v0.as<double>(); c.v0_alt = B.v0.as<double>();
+  c.rho0 = A.rho0.as<double>(); c.rho0_alt = B.rho0.as<double>();
+  c.orig = A.orig.as<int>(); c.orig_alt = B.orig.as<int>();
+  for (DBuf* b : {&c.cs, &c.pq, &c.pp, &c.gamma_s, &c.phi_s, &c.phi2_s}) TIT_CUDA_OK(c, b->ensure(n * 8));
+  for (DBuf* b : {&c.N_s, &c.dr_s, &c.gr_s}) TIT_CUDA_OK(c, b->ensure(n * D * 8));
+  TIT_CUDA_OK(c, c.gv_s.ensure(n * D * D * 8));
+  for (DBuf* b : {&c.cell_id, &c.slot, &c.tmp_perm, &c.perm}) TIT_CUDA_OK(c, b->ensure(n * 4));
+  const size_t nx = std::max<size_t>(c.nx, 1);
+  TIT_CUDA_OK(c, c.gamma_fixed.ensure(nx * 8));
+  TIT_CUDA_OK(c, c.gg_fixed.ensure(nx * D * 8));
+  TIT_CUDA_OK(c, c.rho_fx.ensure(nx * 8));
+  TIT_CUDA_OK(c, c.p_fx.ensure(nx * 8));
+  for (int f = 0; f < F_COUNT; ++f) {
+    const size_t bytes = n * size_t(field_width(f, c.dim)) * 8;
+    TIT_CUDA_OK(c, c.out[f].ensure(bytes));
+    TIT_CUDA_OK(c, cudaMemsetAsync(c.out[f].p, 0, bytes, c.stream));
+  }
+  TIT_CUDA_OK(c, c.staging.ensure(n * D * D * 8));
+  TIT_CUDA_OK(c, c.scalars.ensure(64));
+  TIT_CUDA_OK(c, cudaMemsetAsync(c.scalars.p, 0, 64, c.stream));
+  // Zero state, identity order.
+  TIT_CUDA_OK(c, cudaMemsetAsync(c.r, 0, n * D * 8, c.stream));
+  TIT_CUDA_OK(c, cudaMemsetAsync(c.v, 0, n * D * 8, c.stream));
+  TIT_CUDA_OK(c, cudaMemsetAsync(c.rho, 0, n * 8, c.stream));
+  TIT_CUDA_OK(c, cudaMemsetAsync(c.m, 0, n * 8, c.stream));
+  std::vector<int> id(c.n);
+  for (size_t i = 0; i < c.n; ++i) id[i] = int(i);
+  if (c.n) TIT_CUDA_OK(c, cudaMemcpyAsync(c.orig, id.data(), c.n * 4, cudaMemcpyHostToDevice, c.stream));
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  c.sorted_identity = true;
+  c.grid_ready = false;
+  c.fixed_cache_valid = false;
+  c.sized = true;
+  c.prm.nf = int(c.nf); c.prm.nx = int(c.nx); c.prm.n = int(c.n);
+  return 0;
+}
+
+// Host <-> packed conversion honouring stride_bytes.
+void pack_in(const void* host, size_t n, int width, size_t stride, std::vector<double>& out) {
+  out.resize(n * width);
+  const char* p = static_cast<const char*>(host);
+  for (size_t i = 0; i < n; ++i) std::memcpy(&out[i * width], p + i * stride, size_t(width) * 8);
+}
+void pack_out(const std::vector<double>& in, size_t n, int width, size_t stride, void* host) {
+  char* p = static_cast<char*>(host);
+  for (size_t i = 0; i < n; ++i) std::memcpy(p + i * stride, &in[i * width], size_t(width) * 8);
+}
+
+int check_ready(Ctx& c, bool need_particles) {
+  if (!c.params_set) return fail(c, "titgpu_set_params has not been called");
+  if (need_particles && !c.sized) return fail(c, "no particles uploaded");
+  if (need_particles && c.n > 0x7fffffffull / 16) return fail(c, "too many particles for 32-bit indexing");
+  return 0;
+}
+
+}  // namespace
+}  // namespace titgpu
+
+using namespace titgpu;
+
+extern "C" {
+
+const char* titgpu_version(void) { return "titgpu 0.1 (sm_100a)"; }
+
+int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_id, int integrator_id) {
+  if (!out) return 1;
+  *out = nullptr;
+  titgpu_ctx* h = new (std::nothrow) titgpu_ctx();
+  if (!h) return 1;
+  *out = h;  // returned even on failure so that titgpu_last_error() works
+  Ctx& c = h->c;
+  c.device = device; c.dim = dim; c.kernel_id = kernel_id; c.eos_id = eos_id; c.integrator_id = integrator_id;
+  c.vt = get_engine(dim, kernel_id);
+  if (!c.vt) return fail(c, "no engine built for this (dim, kernel_id)");
+  if (eos_id < 0 || eos_id > 1) return fail(c, "bad eos_id");
+  if (integrator_id < 0 || integrator_id > 3) return fail(c, "bad integrator_id");
+  TIT_CUDA_OK(c, cudaSetDevice(device));
+  TIT_CUDA_OK(c, cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.prm.eos = eos_id;
+  return 0;
+}
+
+int titgpu_destroy(titgpu_ctx* h) {
+  if (!h) return 0;
+  Ctx& c = h->c;
+  if (c.stream) { cudaSetDevice(c.device); cudaStreamSynchronize(c.stream); }
+  for (StateBufs& s : c.st)
+    for (DBuf* b : {&s.r, &s.v, &s.rho, &s.m, &s.r0, &s.v0, &s.rho0, &s.orig}) b->release();
+  for (DBuf* b : {&c.cs, &c.pq, &c.pp, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.r_pre, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm, &c.cell_cnt,
+                  &c.cell_start, &c.cub_tmp, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed, &c.rho_fx, &c.p_fx,
+                  &c.staging, &c.scalars})
+    b->release();
+  for (DBuf& b : c.out) b.release();
+  if (c.stream) cudaStreamDestroy(c.stream);
+  delete h;
+  return 0;
+}
+
+const char* titgpu_last_error(const titgpu_ctx* h) { return h ? h->c.err.c_str() : "null context"; }
+
+int titgpu_set_params(titgpu_ctx* h, double g, double mu, double cs0, double rho0, double xi, double hh, double search_hint, double face_hint) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (!c.vt) return fail(c, "context has no engine");
+  if (!(hh > 0)) return fail(c, "kernel width h must be positive");
+  if (!(cs0 > 0) || !(rho0 > 0)) return fail(c, "cs0 and rho0 must be positive");
+  Params& P = c.prm;
+  P.g = g; P.mu = mu; P.cs0 = cs0; P.rho0 = rho0; P.xi = xi; P.h = hh;
+  P.eos = c.eos_id;
+  c.search_hint = search_hint; c.face_hint = face_hint;
+  c.vt->fill_params(c);
+  c.params_set = true;
+  c.grid_ready = false;
+  c.fixed_cache_valid = false;
+  return 0;
+}
+
+int titgpu_set_surface(titgpu_ctx* h, const double* verts, size_t nv, const uint64_t* faces, size_t nf, const double* iv, size_t niv, const uint64_t* ifc, size_t nif) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  const size_t D = size_t(c.dim);
+  for (size_t i = 0; i < nf * D; ++i)
+    if (faces[i] >= nv) return fail(c, "surface face refers to a vertex out of range");
+  for (size_t i = 0; i < nif * D; ++i)
+    if (ifc[i] >= niv) return fail(c, "containment face refers to a vertex out of range");
+  c.h_verts.assign(verts, verts + nv * D);
+  c.h_faces.assign(faces, faces + nf * D);
+  c.h_cverts.assign(iv, iv + niv * D);
+  c.h_cfaces.assign(ifc, ifc + nif * D);
+  c.surface_set = true;
+  c.grid_ready = false;
+  c.fixed_cache_valid = false;
+  return 0;
+}
+
+int titgpu_upload(titgpu_ctx* h, size_t n_fluid, size_t n_fixed, const char* field, const void* host, size_t stride) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (!c.vt) return fail(c, "context has no engine");
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+  const int f = field_by_name(field);
+  if (f < 0) return fail(c, std::string("unknown field '") + field + "'");
+  if (!c.sized || n_fluid != c.nf || n_fixed != c.nx) {
+    c.nf = n_fluid; c.nx = n_fixed; c.n = n_fluid + n_fixed;
+    if (c.n > 0x7fffffffull / 16) return fail(c, "too many particles for 32-bit indexing");
+    if (alloc_particles(c)) return 1;
+  }
+  if (c.n == 0) return 0;
+  const int w = field_width(f, c.dim);
+  if (stride == 0) stride = size_t(w) * 8;
+  if (stride < size_t(w) * 8) return fail(c, "stride_bytes smaller than the field value");
+  std::vector<double> packed;
+  const double* src = static_cast<const double*>(host);
+  if (stride != size_t(w) * 8) { pack_in(host, c.n, w, stride, packed); src = packed.data(); }
+  const size_t bytes = c.n * size_t(w) * 8;
+  const bool is_state = (f == F_r || f == F_v || f == F_rho || f == F_m);
+  if (!is_state) {
+    TIT_CUDA_OK(c, cudaMemcpyAsync(c.out[f].p, src, bytes, cudaMemcpyHostToDevice, c.stream));
+    if (f == F_dv_dt && c.vt->seed_fmax(c)) return 1;
+    TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    return 0;
+  }
+  if (c.sorted_identity) {
+    double* dst = f == F_r ? c.r : f == F_v ? c.v : f == F_rho ? c.rho : c.m;
+    TIT_CUDA_OK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
+  } else {
+    TIT_CUDA_OK(c, cudaMemcpyAsync(c.staging.p, src, bytes, cudaMemcpyHostToDevice, c.stream));
+    if (c.vt->upload_state(c, f, c.staging.as<double>())) return 1;
+  }
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  if (f == F_r) { c.fixed_cache_valid = false; }
+  return 0;
+}
+
+int titgpu_download(titgpu_ctx* h, const char* field, void* host, size_t stride) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (!c.sized) return fail(c, "no particles uploaded");
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+  const int f = field_by_name(field);
+  if (f < 0) return fail(c, std::string("unknown field '") + field + "'");
+  if (c.n == 0) return 0;
+  const int w = field_width(f, c.dim);
+  if (stride == 0) stride = size_t(w) * 8;
+  if (stride < size_t(w) * 8) return fail(c, "stride_bytes smaller than the field value");
+  const size_t bytes = c.n * size_t(w) * 8;
+  const bool is_state = (f == F_r || f == F_v || f == F_rho || f == F_m);
+  const double* src = c.out[f].as<double>();
+  if (is_state) {
+    if (c.vt->download_state(c, f, c.staging.as<double>())) return 1;
+    src = c.staging.as<double>();
+  }
+  if (stride == size_t(w) * 8) {
+    TIT_CUDA_OK(c, cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  } else {
+    std::vector<double> packed(c.n * w);
+    TIT_CUDA_OK(c, cudaMemcpyAsync(packed.data(), src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+    pack_out(packed, c.n, w, stride, host);
+  }
+  return 0;
+}
+
+#define TITGPU_ENTER(need_particles)                 \
+  if (!h) return 1;                                  \
+  Ctx& c = h->c;                                     \
+  if (!c.vt) return fail(c, "context has no engine"); \
+  if (check_ready(c, need_particles)) return 1;      \
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+
+#define TITGPU_LEAVE()                                   \
+  TIT_CUDA_OK(c, cudaGetLastError());                    \
+  return 0;
+
+int titgpu_initialize(titgpu_ctx* h) {
+  TITGPU_ENTER(true)
+  if (c.vt->initialize(c)) return 1;
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  TITGPU_LEAVE()
+}
+int titgpu_prepare(titgpu_ctx* h) {
+  TITGPU_ENTER(true)
+  if (c.vt->prepare(c, true)) return 1;
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  TITGPU_LEAVE()
+}
+int titgpu_rhs_only(titgpu_ctx* h) {
+  TITGPU_ENTER(true)
+  if (c.vt->rhs_only(c)) return 1;
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  TITGPU_LEAVE()
+}
+int titgpu_step(titgpu_ctx* h, int nsteps, double* dt_last) {
+  TITGPU_ENTER(true)
+  if (nsteps < 0) return fail(c, "nsteps must be non-negative");
+  if (c.vt->step(c, nsteps)) return 1;
+  double dt = 0;
+  TIT_CUDA_OK(c, cudaMemcpyAsync(&dt, c.scalars.p, 8, cudaMemcpyDeviceToHost, c.stream));
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  if (dt_last) *dt_last = dt;
+  TITGPU_LEAVE()
+}
+int titgpu_neighbors(titgpu_ctx* h, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz) {
+  TITGPU_ENTER(true)
+  if (!nnz) return fail(c, "nnz must not be null");
+  const int rc = c.vt->neighbors(c, off, cols, cap, nnz);
+  if (rc) return rc;
+  TITGPU_LEAVE()
+}
+int titgpu_synchronize(titgpu_ctx* h) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  return 0;
+}
+unsigned long long titgpu_launch_count(const titgpu_ctx* h) { return h ? h->c.launches : 0; }
+void* titgpu_stream(titgpu_ctx* h) { return h ? (void*)h->c.stream : nullptr; }
+
+}  // extern "C"
