@@ -99,6 +99,18 @@ TITGPU_API int titgpu_synchronize(titgpu_ctx* ctx);
 TITGPU_API unsigned long long titgpu_launch_count(const titgpu_ctx* ctx);
 /* The CUDA stream the context launches on (cudaStream_t), for event timing. */
 TITGPU_API void* titgpu_stream(titgpu_ctx* ctx);
+/* Per-kernel device timing (the analogue of the reference's TIT_PROFILE_SECTION
+ * stopwatches, core/profiler.hpp:42-44): when enabled, every kernel launch is
+ * bracketed by CUDA events on the context's stream and the durations are summed
+ * per kernel name. `titgpu_profile_get` returns entry `index` (0 <=
+ * index < titgpu_profile_count). */
+TITGPU_API int titgpu_profile_enable(titgpu_ctx* ctx, int on);
+TITGPU_API int titgpu_profile_reset(titgpu_ctx* ctx);
+TITGPU_API int titgpu_profile_count(titgpu_ctx* ctx);
+TITGPU_API int titgpu_profile_get(titgpu_ctx* ctx, int index, const char** name, unsigned long long* launches, double* total_ms);
+/* Measured FP64 FMA throughput of the device (dependent-chain-free DFMA loop on
+ * every SM), in TFLOP/s: the denominator of the FP64-pipe roofline. */
+TITGPU_API int titgpu_measure_fp64_peak(titgpu_ctx* ctx, double* tflops);
 /* Library version string. */
 TITGPU_API const char* titgpu_version(void);
 

@@ -68,6 +68,13 @@ def test_neighbors_dam_break_lattice(oracle, n_col):
     assert cnt[: case.n_fluid].max() == 49  # 49 incl. self on the 2-D lattice
 
 
+def case_3d(n_col=6):
+    """Generic positions: the 3-D wall integrals of the reference are evaluated at
+    rounding-noise level when a face touches the support sphere exactly (see
+    cases.dam_break_3d), so parity is checked off the lattice."""
+    return cases.dam_break_3d(n_col, wall_ratio=0.93, jitter=0.1)
+
+
 def test_neighbors_3d_lattice(oracle):
     case = cases.dam_break_3d(6)
     g, c = make_pair(oracle, case)
@@ -167,11 +174,11 @@ def test_drift_20_steps_2d(oracle):
 
 
 def test_rhs_parity_3d(oracle):
-    check_rhs(oracle, cases.dam_break_3d(6))
+    check_rhs(oracle, case_3d())
 
 
 def test_one_step_parity_3d(oracle):
-    check_step(oracle, cases.dam_break_3d(6))
+    check_step(oracle, case_3d())
 
 
 def test_strided_upload_download(oracle):

@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
     "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
+    "titgpu_profile_enable", "titgpu_profile_reset", "titgpu_profile_count", "titgpu_profile_get", "titgpu_measure_fp64_peak",
 ]
 
 
@@ -67,6 +68,11 @@ def load_library() -> C.CDLL:
     lib.titgpu_stream.argtypes = [vp]
     lib.titgpu_stream.restype = vp
     lib.titgpu_version.restype = C.c_char_p
+    lib.titgpu_profile_enable.argtypes = [vp, C.c_int]
+    lib.titgpu_profile_reset.argtypes = [vp]
+    lib.titgpu_profile_count.argtypes = [vp]
+    lib.titgpu_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_ulonglong), C.POINTER(d)]
+    lib.titgpu_measure_fp64_peak.argtypes = [vp, C.POINTER(d)]
     _lib = lib
     return lib
 
@@ -172,6 +178,26 @@ class Solver:
 
     def synchronize(self):
         self._ck(self.lib.titgpu_synchronize(self.h), "titgpu_synchronize")
+
+    def profile(self, on=True):
+        self._ck(self.lib.titgpu_profile_enable(self.h, int(on)), "titgpu_profile_enable")
+
+    def profile_reset(self):
+        self._ck(self.lib.titgpu_profile_reset(self.h), "titgpu_profile_reset")
+
+    def profile_read(self):
+        """{kernel name: (launches, total device ms)} since the last reset."""
+        out = {}
+        for i in range(self.lib.titgpu_profile_count(self.h)):
+            name, cnt, ms = C.c_char_p(), C.c_ulonglong(), C.c_double()
+            self._ck(self.lib.titgpu_profile_get(self.h, i, C.byref(name), C.byref(cnt), C.byref(ms)), "titgpu_profile_get")
+            out[name.value.decode()] = (int(cnt.value), float(ms.value))
+        return out
+
+    def measure_fp64_peak(self):
+        t = C.c_double(0)
+        self._ck(self.lib.titgpu_measure_fp64_peak(self.h, C.byref(t)), "titgpu_measure_fp64_peak")
+        return t.value
 
     @property
     def launch_count(self):

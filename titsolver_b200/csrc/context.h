@@ -103,6 +103,45 @@ struct Ctx {
   // Counters.
   unsigned long long launches = 0;
 
+  // Optional per-kernel timing (titgpu_profile_*): CUDA events on `stream`
+  // around every launch, folded into per-name totals after each API call.
+  struct ProfPending { const char* name; cudaEvent_t beg, end; };
+  struct ProfTotal { std::string name; unsigned long long count = 0; double ms = 0; };
+  bool prof_on = false;
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<ProfTotal> prof_totals;
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  cudaEvent_t prof_begin(const char* name) {
+    if (!prof_on) return nullptr;
+    ProfPending p{name, prof_event(), prof_event()};
+    cudaEventRecord(p.beg, stream);
+    prof_pending.push_back(p);
+    return p.end;
+  }
+  void prof_end(cudaEvent_t e) { if (e) cudaEventRecord(e, stream); }
+  // Requires the stream to be idle (call after cudaStreamSynchronize).
+  void prof_fold() {
+    for (const ProfPending& p : prof_pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, p.beg, p.end) == cudaSuccess) {
+        ProfTotal* t = nullptr;
+        for (ProfTotal& q : prof_totals) if (q.name == p.name) { t = &q; break; }
+        if (!t) { prof_totals.push_back(ProfTotal{p.name}); t = &prof_totals.back(); }
+        t->count++;
+        t->ms += ms;
+      }
+      prof_pool.push_back(p.beg);
+      prof_pool.push_back(p.end);
+    }
+    prof_pending.clear();
+  }
+
   std::string err;
 };
 

@@ -266,6 +266,7 @@ int titgpu_download(titgpu_ctx* h, const char* field, void* host, size_t stride)
 
 #define TITGPU_LEAVE()                                   \
   TIT_CUDA_OK(c, cudaGetLastError());                    \
+  c.prof_fold();                                         \
   return 0;
 
 int titgpu_initialize(titgpu_ctx* h) {
@@ -310,6 +311,74 @@ int titgpu_synchronize(titgpu_ctx* h) {
   TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
   return 0;
 }
+int titgpu_profile_enable(titgpu_ctx* h, int on) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  c.prof_fold();
+  c.prof_on = on != 0;
+  return 0;
+}
+int titgpu_profile_reset(titgpu_ctx* h) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  c.prof_fold();
+  c.prof_totals.clear();
+  return 0;
+}
+int titgpu_profile_count(titgpu_ctx* h) { return h ? int(h->c.prof_totals.size()) : 0; }
+int titgpu_profile_get(titgpu_ctx* h, int i, const char** name, unsigned long long* launches, double* total_ms) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (i < 0 || size_t(i) >= c.prof_totals.size()) return fail(c, "profile index out of range");
+  if (name) *name = c.prof_totals[size_t(i)].name.c_str();
+  if (launches) *launches = c.prof_totals[size_t(i)].count;
+  if (total_ms) *total_ms = c.prof_totals[size_t(i)].ms;
+  return 0;
+}
+
+// 8 independent FMA chains per thread: enough ILP to saturate the FP64 pipe.
+static __global__ void k_fp64_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+int titgpu_measure_fp64_peak(titgpu_ctx* h, double* tflops) {
+  if (!h || !tflops) return 1;
+  Ctx& c = h->c;
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+  int sms = 0;
+  TIT_CUDA_OK(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+  double* out = nullptr;
+  TIT_CUDA_OK(c, cudaMalloc(&out, size_t(blocks) * threads * 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, c.stream);
+    k_fp64_peak<<<blocks, threads, 0, c.stream>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, c.stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+    c.launches++;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  TIT_CUDA_OK(c, cudaGetLastError());
+  *tflops = 2.0 * 8.0 * double(iters) * double(blocks) * threads / (double(best) * 1e-3) / 1e12;
+  return 0;
+}
+
 unsigned long long titgpu_launch_count(const titgpu_ctx* h) { return h ? h->c.launches : 0; }
 void* titgpu_stream(titgpu_ctx* h) { return h ? (void*)h->c.stream : nullptr; }
 
