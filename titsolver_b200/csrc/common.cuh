@@ -138,12 +138,18 @@ constexpr double kCShift = 0.2;
 constexpr double kPhiMax = 1.0;
 constexpr double kPhiMin = DBL_MIN;
 
-// Uniform cell grid used for both the particle hash and the static face index.
+// Particle cells per support radius: a particle's neighbours lie within +-KC_
+// cells per axis.
+constexpr int KC_ = 2;
+
+// Uniform cell grid. Two instances share one origin: the particle hash (cells
+// of radius / KC_) and the static face index (cells of one radius). The face
+// cell size is radius * (1 + 2^-20) so that points exactly one radius apart
+// (the initial lattice) are always within the expected cell distance despite
+// rounding of the quotient.
 struct GridDesc {
   double org[3];
-  double cinv;  // 1 / cell size; cell size = radius * (1 + 2^-20) so that
-                // particles exactly one radius apart (the initial lattice) are
-                // always in adjacent cells despite rounding of the quotient.
+  double cinv;  // 1 / cell size
   int nc[3];
   int ncells;
 };
@@ -158,24 +164,36 @@ struct Params {
   double cos_fov2;  // cos(pi/4)^2 as evaluated in double (fluid_equations.hpp:406-407)
   int eos;
   int nf, nx, n;
-  GridDesc grid;
+  float pre_thr;  // FP32 pre-filter threshold on the squared distance in cell units
+  float oor;      // |grid coordinate| beyond which the FP32 pre-filter is bypassed
+  GridDesc grid;   // particle hash
+  GridDesc fgrid;  // face index + per-cell wall / containment flags
 };
+
+// x^e: small integer exponents (the Tait defaults xi = 7 -> 7, 6, 3) by repeated
+// multiplication, anything else through pow().
+TIT_HD double pow_fast(double x, double e) {
+  if (e == 7.0) { const double x2 = x * x, x4 = x2 * x2; return x4 * x2 * x; }
+  if (e == 6.0) { const double x2 = x * x; return x2 * x2 * x2; }
+  if (e == 3.0) return x * x * x;
+  return pow(x, e);
+}
 
 // Equation of state (sph/equation_of_state.hpp:19-122).
 struct Eos {
   TIT_HD static double p(const Params& P, double rho) {
     if (P.eos == 1) return P.cs0 * P.cs0 * (rho - P.rho0);
     const double B = P.rho0 * (P.cs0 * P.cs0) / P.xi;
-    return B * (pow(rho / P.rho0, P.xi) - 1.0);
+    return B * (pow_fast(rho / P.rho0, P.xi) - 1.0);
   }
   TIT_HD static double cs(const Params& P, double rho) {
     if (P.eos == 1) return P.cs0;
-    return P.cs0 * pow(rho / P.rho0, (P.xi - 1.0) / 2.0);
+    return P.cs0 * pow_fast(rho / P.rho0, (P.xi - 1.0) / 2.0);
   }
   TIT_HD static double H(const Params& P, double rho) {
     if (P.eos == 1) return P.cs0 * P.cs0 * log(rho / P.rho0);
     const double x1 = P.xi - 1.0;
-    return P.cs0 * P.cs0 * (pow(rho / P.rho0, x1) - 1.0) / x1;
+    return P.cs0 * P.cs0 * (pow_fast(rho / P.rho0, x1) - 1.0) / x1;
   }
   TIT_HD static double rho_from_H(const Params& P, double Hh) {
     if (P.eos == 1) return P.rho0 * exp(Hh / (P.cs0 * P.cs0));

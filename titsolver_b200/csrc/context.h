@@ -46,16 +46,11 @@ struct DBuf {
   template<class T> T* as() const { return static_cast<T*>(p); }
 };
 
-// Sorted-order particle state; two copies (ping-pong for the cell reorder and
-// for the fused RHS + update pass).
-struct StateBufs {
-  DBuf r, v, rho, m, r0, v0, rho0, orig;
-};
-
 struct EngineVTable;
 
 struct Ctx {
   int device = 0, dim = 2, kernel_id = 4, eos_id = 0, integrator_id = 3;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   const EngineVTable* vt = nullptr;
   Params prm{};
@@ -64,23 +59,27 @@ struct Ctx {
   size_t nf = 0, nx = 0, n = 0;
   double search_hint = 0, face_hint = 0;
 
-  StateBufs st[2];
-  int cur = 0;  // st[cur] holds r/v/rho/...; individual fields may be swapped, see ptrs below
-  // Current pointers (fields swap independently).
-  double *r = nullptr, *v = nullptr, *rho = nullptr, *m = nullptr, *r0 = nullptr, *v0 = nullptr, *rho0 = nullptr;
-  int* orig = nullptr;
-  double *r_alt = nullptr, *v_alt = nullptr, *rho_alt = nullptr, *m_alt = nullptr, *r0_alt = nullptr, *v0_alt = nullptr, *rho0_alt = nullptr;
-  int* orig_alt = nullptr;
+  // Packed particle records in sorted order (see engine.cuh): A = position +
+  // density (+ mass in 2-D), B = velocity (+ mass in 3-D); A0 / B0 = the state
+  // at the beginning of the step (SSPRK). Each exists twice (ping-pong for the
+  // cell reorder and for the fused RHS + update pass); the pointers swap
+  // independently.
+  DBuf bufA[4], bufB[4], buf_orig[2];
+  double4 *A = nullptr, *B = nullptr, *A_alt = nullptr, *B_alt = nullptr;
+  double4 *A0 = nullptr, *B0 = nullptr, *A0_alt = nullptr, *B0_alt = nullptr;
+  int *orig = nullptr, *orig_alt = nullptr;
 
   // Per-sorted-particle derived data.
-  DBuf cs, pq, pp;               // sound speed, p / rho^2, p
-  DBuf gamma_s, N_s, phi_s, phi2_s, dr_s, gv_s, gr_s, r_pre;  // post-integration scratch
+  DBuf C;                        // {cs, p / rho^2, 1 / rho, p}
+  DBuf F;                        // float4 grid coordinates + flags (FP32 pre-filter)
+  DBuf gamma_w, gg_w, wsum;      // wall pass: gamma, grad gamma, face sums of the consumer
+  DBuf gamma_s, N_s, phi_s, phi2_s, dr_s, gv_s, gr_s, fs_flag;  // post-integration scratch
 
   // Hash / sort scratch.
   DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp;
 
   // Static boundary.
-  DBuf frames, fcell_start, fcell_faces, face_cells;
+  DBuf frames, fcell_start, fcell_faces, face_cells, fflag;
   size_t nfaces = 0;
   DBuf cverts, cfaces;
   size_t ncfaces = 0;

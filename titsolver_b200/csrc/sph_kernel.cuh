@@ -53,6 +53,11 @@ struct SphKernel {
     return P.w_val * P.hinv * KG::unit_deriv(P.hinv * rn) / rn;
   }
 
+  // Same with 1 / |x| supplied (the pair loops get it from one rsqrt).
+  TIT_HD static double grad_coef_rinv(const Params& P, double rn, double rinv) {
+    return P.w_val * P.hinv * KG::unit_deriv(P.hinv * rn) * rinv;
+  }
+
   // ---- 2-D: clipped segment integral (kernel.hpp:287-314) ----
   template<bool Anti, int I>
   TIT_HD static double seg_prim(double eta, double z, bool eta_tiny) {

@@ -34,31 +34,19 @@ int fail(Ctx& c, const std::string& msg) {
 
 int alloc_particles(Ctx& c) {
   const size_t n = std::max<size_t>(c.n, 1), D = size_t(c.dim);
-  auto pair = [&](DBuf& a, DBuf& b, size_t bytes) -> cudaError_t {
-    cudaError_t e = a.ensure(bytes);
-    if (e != cudaSuccess) return e;
-    return b.ensure(bytes);
-  };
-  StateBufs &A = c.st[0], &B = c.st[1];
-  TIT_CUDA_OK(c, pair(A.r, B.r, n * D * 8));
-  TIT_CUDA_OK(c, pair(A.v, B.v, n * D * 8));
-  TIT_CUDA_OK(c, pair(A.rho, B.rho, n * 8));
-  TIT_CUDA_OK(c, pair(A.m, B.m, n * 8));
-  TIT_CUDA_OK(c, pair(A.r0, B.r0, n * D * 8));
-  TIT_CUDA_OK(c, pair(A.v0, B.v0, n * D * 8));
-  TIT_CUDA_OK(c, pair(A.rho0, B.rho0, n * 8));
-  TIT_CUDA_OK(c, pair(A.orig, B.orig, n * 4));
-  c.r = A.r.as<double>(); c.r_alt = B.r.as<double>();
-  c.v = A.v.as<double>(); c.v_alt = B.v.as<double>();
-  c.rho = A.rho.as<double>(); c.rho_alt = B.rho.as<double>();
-  c.m = A.m.as<double>(); c.m_alt = B.m.as<double>();
-  c.r0 = A.r0.as<double>(); c.r0_alt = B.r0.as<double>();
-  c.v0 = A.v0.as<double>(); c.v0_alt = B.v0.as<double>();
-  c.rho0 = A.rho0.as<double>(); c.rho0_alt = B.rho0.as<double>();
-  c.orig = A.orig.as<int>(); c.orig_alt = B.orig.as<int>();
-  for (DBuf* b : {&c.cs, &c.pq, &c.pp, &c.gamma_s, &c.phi_s, &c.phi2_s}) TIT_CUDA_OK(c, b->ensure(n * 8));
-  for (DBuf* b : {&c.N_s, &c.dr_s, &c.gr_s}) TIT_CUDA_OK(c, b->ensure(n * D * 8));
+  for (DBuf& b : c.bufA) TIT_CUDA_OK(c, b.ensure(n * sizeof(double4)));
+  for (DBuf& b : c.bufB) TIT_CUDA_OK(c, b.ensure(n * sizeof(double4)));
+  for (DBuf& b : c.buf_orig) TIT_CUDA_OK(c, b.ensure(n * 4));
+  c.A = c.bufA[0].as<double4>(); c.A_alt = c.bufA[1].as<double4>(); c.A0 = c.bufA[2].as<double4>(); c.A0_alt = c.bufA[3].as<double4>();
+  c.B = c.bufB[0].as<double4>(); c.B_alt = c.bufB[1].as<double4>(); c.B0 = c.bufB[2].as<double4>(); c.B0_alt = c.bufB[3].as<double4>();
+  c.orig = c.buf_orig[0].as<int>(); c.orig_alt = c.buf_orig[1].as<int>();
+  TIT_CUDA_OK(c, c.C.ensure(n * sizeof(double4)));
+  TIT_CUDA_OK(c, c.F.ensure(n * sizeof(float4)));
+  for (DBuf* b : {&c.gamma_w, &c.gamma_s, &c.phi_s, &c.phi2_s}) TIT_CUDA_OK(c, b->ensure(n * 8));
+  for (DBuf* b : {&c.gg_w, &c.N_s, &c.dr_s, &c.gr_s}) TIT_CUDA_OK(c, b->ensure(n * D * 8));
   TIT_CUDA_OK(c, c.gv_s.ensure(n * D * D * 8));
+  TIT_CUDA_OK(c, c.wsum.ensure(n * (2 * D + 2 * D * D) * 8));
+  TIT_CUDA_OK(c, c.fs_flag.ensure(n));
   for (DBuf* b : {&c.cell_id, &c.slot, &c.tmp_perm, &c.perm}) TIT_CUDA_OK(c, b->ensure(n * 4));
   const size_t nx = std::max<size_t>(c.nx, 1);
   TIT_CUDA_OK(c, c.gamma_fixed.ensure(nx * 8));
@@ -74,10 +62,8 @@ int alloc_particles(Ctx& c) {
   TIT_CUDA_OK(c, c.scalars.ensure(64));
   TIT_CUDA_OK(c, cudaMemsetAsync(c.scalars.p, 0, 64, c.stream));
   // Zero state, identity order.
-  TIT_CUDA_OK(c, cudaMemsetAsync(c.r, 0, n * D * 8, c.stream));
-  TIT_CUDA_OK(c, cudaMemsetAsync(c.v, 0, n * D * 8, c.stream));
-  TIT_CUDA_OK(c, cudaMemsetAsync(c.rho, 0, n * 8, c.stream));
-  TIT_CUDA_OK(c, cudaMemsetAsync(c.m, 0, n * 8, c.stream));
+  for (DBuf& b : c.bufA) TIT_CUDA_OK(c, cudaMemsetAsync(b.p, 0, n * sizeof(double4), c.stream));
+  for (DBuf& b : c.bufB) TIT_CUDA_OK(c, cudaMemsetAsync(b.p, 0, n * sizeof(double4), c.stream));
   std::vector<int> id(c.n);
   for (size_t i = 0; i < c.n; ++i) id[i] = int(i);
   if (c.n) TIT_CUDA_OK(c, cudaMemcpyAsync(c.orig, id.data(), c.n * 4, cudaMemcpyHostToDevice, c.stream));
@@ -131,6 +117,7 @@ int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_
   if (integrator_id < 0 || integrator_id > 3) return fail(c, "bad integrator_id");
   TIT_CUDA_OK(c, cudaSetDevice(device));
   TIT_CUDA_OK(c, cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  TIT_CUDA_OK(c, cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
   c.prm.eos = eos_id;
   return 0;
 }
@@ -139,12 +126,15 @@ int titgpu_destroy(titgpu_ctx* h) {
   if (!h) return 0;
   Ctx& c = h->c;
   if (c.stream) { cudaSetDevice(c.device); cudaStreamSynchronize(c.stream); }
-  for (StateBufs& s : c.st)
-    for (DBuf* b : {&s.r, &s.v, &s.rho, &s.m, &s.r0, &s.v0, &s.rho0, &s.orig}) b->release();
-  for (DBuf* b : {&c.cs, &c.pq, &c.pp, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.r_pre, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm, &c.cell_cnt,
-                  &c.cell_start, &c.cub_tmp, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed, &c.rho_fx, &c.p_fx,
-                  &c.staging, &c.scalars})
+  for (DBuf& b : c.bufA) b.release();
+  for (DBuf& b : c.bufB) b.release();
+  for (DBuf& b : c.buf_orig) b.release();
+  for (DBuf* b : {&c.C, &c.F, &c.gamma_w, &c.gg_w, &c.wsum, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.fs_flag, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm,
+                  &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
+                  &c.rho_fx, &c.p_fx, &c.staging, &c.scalars})
     b->release();
+  for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
+  for (auto& p : c.prof_pending) { cudaEventDestroy(p.beg); cudaEventDestroy(p.end); }
   for (DBuf& b : c.out) b.release();
   if (c.stream) cudaStreamDestroy(c.stream);
   delete h;
@@ -215,14 +205,10 @@ int titgpu_upload(titgpu_ctx* h, size_t n_fluid, size_t n_fixed, const char* fie
     TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
     return 0;
   }
-  if (c.sorted_identity) {
-    double* dst = f == F_r ? c.r : f == F_v ? c.v : f == F_rho ? c.rho : c.m;
-    TIT_CUDA_OK(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream));
-  } else {
-    TIT_CUDA_OK(c, cudaMemcpyAsync(c.staging.p, src, bytes, cudaMemcpyHostToDevice, c.stream));
-    if (c.vt->upload_state(c, f, c.staging.as<double>())) return 1;
-  }
+  TIT_CUDA_OK(c, cudaMemcpyAsync(c.staging.p, src, bytes, cudaMemcpyHostToDevice, c.stream));
+  if (c.vt->upload_state(c, f, c.staging.as<double>())) return 1;
   TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  c.prof_fold();
   if (f == F_r) { c.fixed_cache_valid = false; }
   return 0;
 }
