@@ -15,6 +15,9 @@
 #ifndef TIT_HD
 #define TIT_HD __host__ __device__ __forceinline__
 #endif
+#ifndef TIT_HDN
+#define TIT_HDN __host__ __device__ __noinline__
+#endif
 
 namespace titgpu {
 

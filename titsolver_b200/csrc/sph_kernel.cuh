@@ -58,17 +58,23 @@ struct SphKernel {
     return P.w_val * P.hinv * KG::unit_deriv(P.hinv * rn) * rinv;
   }
 
+  // The wall integrals are deliberately NOT inlined into their callers: each
+  // primitive carries an atan2 and a log1p, and fully unrolled (3 edges x 3
+  // pieces x 2 end points x 2 kinds) the wall kernel grew to ~40 k instructions
+  // and stalled on instruction fetch. `anti` selects the antigradient
+  // primitive at run time so that both kinds share one copy of the code.
+
   // ---- 2-D: clipped segment integral (kernel.hpp:287-314) ----
-  template<bool Anti, int I>
-  TIT_HD static double seg_prim(double eta, double z, bool eta_tiny) {
+  template<int I>
+  TIT_HDN static double seg_prim(bool anti, double eta, double z, bool eta_tiny) {
     const double rho = sqrt(fma(z, z, eta * eta));
     const double A = atan2(z, eta);
     const double L = eta_tiny ? 0.0 : copysign(log1p((fabs(z) + z * z / (rho + eta)) / eta), z);
-    if constexpr (Anti) return KG::template seg_antigrad<I>(eta, z, rho, A, L);
-    else return KG::template seg_flux<I>(eta, z, rho, A, L);
+    if (anti) return KG::template seg_antigrad<I>(eta, z, rho, A, L);
+    return KG::template seg_flux<I>(eta, z, rho, A, L);
   }
-  template<bool Anti, int I>
-  TIT_HD static double seg_piece(const Params& P, double eta, double z_min, double z_max) {
+  template<int I>
+  TIT_HD static double seg_piece(const Params& P, bool anti, double eta, double z_min, double z_max) {
     const double c = KG::cutoff(I);
     if (eta >= c) return 0.0;
     const double z_clip = sqrt(c * c - eta * eta);
@@ -76,72 +82,84 @@ struct SphKernel {
     const double z_hi = fmin(z_max, +z_clip);
     if (z_lo >= z_hi) return 0.0;
     const bool et = fabs(eta) <= P.tiny;
-    return seg_prim<Anti, I>(eta, z_hi, et) - seg_prim<Anti, I>(eta, z_lo, et);
+    return seg_prim<I>(anti, eta, z_hi, et) - seg_prim<I>(anti, eta, z_lo, et);
   }
-  template<bool Anti, int I = 0>
-  TIT_HD static double seg_integral(const Params& P, double eta, double z_min, double z_max) {
+  template<int I = 0>
+  TIT_HD static double seg_integral(const Params& P, bool anti, double eta, double z_min, double z_max) {
     if constexpr (I >= KG::num_pieces) return 0.0;
-    else return seg_piece<Anti, I>(P, eta, z_min, z_max) + seg_integral<Anti, I + 1>(P, eta, z_min, z_max);
+    else return seg_piece<I>(P, anti, eta, z_min, z_max) + seg_integral<I + 1>(P, anti, eta, z_min, z_max);
   }
 
   // ---- 3-D: clipped triangle integral (kernel.hpp:319-399) ----
-  template<bool Anti, int I>
-  TIT_HD static double line_prim(const Params& P, double eta, double delta, double delta_sqr, double beta_sqr, double beta, double z) {
+  template<int I>
+  TIT_HDN static double line_prim(double tiny, bool anti, double eta, double delta, double delta_sqr, double beta_sqr, double beta, double z) {
     const double rho = sqrt(fma(z, z, beta_sqr));
-    const double A = fabs(delta) <= P.tiny ? 0.0 : atan2(delta * z * (rho - eta), fma(delta_sqr, rho, z * z * eta));
-    const double L = fabs(beta) <= P.tiny ? 0.0 : copysign(log1p((fabs(z) + z * z / (rho + beta)) / beta), z);
-    if constexpr (Anti) return KG::template tri_antigrad_line<I>(eta, delta, z, rho, A, L);
-    else return KG::template tri_flux_line<I>(eta, delta, z, rho, A, L);
+    const double A = fabs(delta) <= tiny ? 0.0 : atan2(delta * z * (rho - eta), fma(delta_sqr, rho, z * z * eta));
+    const double L = fabs(beta) <= tiny ? 0.0 : copysign(log1p((fabs(z) + z * z / (rho + beta)) / beta), z);
+    if (anti) return KG::template tri_antigrad_line<I>(eta, delta, z, rho, A, L);
+    return KG::template tri_flux_line<I>(eta, delta, z, rho, A, L);
   }
-  template<bool Anti, int I>
-  TIT_HD static double tri_edge(const Params& P, double eta, double radius_sqr, double sector, const double* p0, const double* p1) {
-    const double ex = p1[0] - p0[0], ey = p1[1] - p0[1];
+  // One edge p0 -> p1 of the projected triangle: the line is cut at its (up to
+  // two) intersections with the support circle; pieces inside the circle use the
+  // line primitive, pieces outside contribute the sector term.
+  template<int I>
+  TIT_HDN static double tri_edge(double tiny, bool anti, double eta, double radius_sqr, double sector, double p0x, double p0y, double p1x, double p1y) {
+    const double ex = p1x - p0x, ey = p1y - p0y;
     const double len2 = ex * ex + ey * ey;
-    if (len2 <= P.tiny2) return 0.0;
+    if (len2 <= tiny * tiny) return 0.0;
     const double len = sqrt(len2);
     const double tx = ex / len, ty = ey / len;
-    const double delta = p0[0] * ty - p0[1] * tx;  // det(p0, tangent)
+    const double delta = p0x * ty - p0y * tx;  // det(p0, tangent)
     const double delta_sqr = delta * delta;
     const double beta_sqr = eta * eta + delta_sqr;
     const double beta = sqrt(beta_sqr);
-    const double z_start = p0[0] * tx + p0[1] * ty;
+    const double z_start = p0x * tx + p0y * ty;
     const double z_finish = z_start + len;
-    double zs[4];
-    int nz = 0;
-    zs[nz++] = z_start;
+    // Cut points (kernel.hpp:371-380); an absent cut collapses its piece to zero
+    // length, which the `tiny` test below skips just like a short piece.
+    double m1 = z_start, m2 = z_start;
     if (radius_sqr > delta_sqr) {
       const double z_clip = sqrt(radius_sqr - delta_sqr);
-      if (z_start < -z_clip && -z_clip < z_finish) zs[nz++] = -z_clip;
-      if (z_start < +z_clip && +z_clip < z_finish) zs[nz++] = +z_clip;
+      if (z_start < -z_clip && -z_clip < z_finish) m1 = -z_clip;
+      m2 = m1;
+      if (z_start < +z_clip && +z_clip < z_finish) m2 = +z_clip;
     }
-    zs[nz++] = z_finish;
     double result = 0.0;
-    for (int i = 0; i + 1 < nz; ++i) {
-      const double z_lo = zs[i], z_hi = zs[i + 1];
-      if (fabs(z_hi - z_lo) <= P.tiny) continue;
-      const double zm = 0.5 * (z_lo + z_hi);
-      if (zm * zm + delta_sqr < radius_sqr) {
-        result += line_prim<Anti, I>(P, eta, delta, delta_sqr, beta_sqr, beta, z_hi) - line_prim<Anti, I>(P, eta, delta, delta_sqr, beta_sqr, beta, z_lo);
-      } else {
-        result += sector * atan2(delta * (z_hi - z_lo), fma(z_lo, z_hi, delta_sqr));
+    double z_lo = z_start;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+      const double z_hi = k == 0 ? m1 : k == 1 ? m2 : z_finish;
+      if (fabs(z_hi - z_lo) > tiny) {
+        const double zm = 0.5 * (z_lo + z_hi);
+        if (zm * zm + delta_sqr < radius_sqr) {
+          result += line_prim<I>(tiny, anti, eta, delta, delta_sqr, beta_sqr, beta, z_hi) - line_prim<I>(tiny, anti, eta, delta, delta_sqr, beta_sqr, beta, z_lo);
+        } else {
+          result += sector * atan2(delta * (z_hi - z_lo), fma(z_lo, z_hi, delta_sqr));
+        }
       }
+      if (z_hi != z_lo) z_lo = z_hi;
     }
     return result;
   }
-  template<bool Anti, int I>
-  TIT_HD static double tri_piece(const Params& P, double eta, const double* a, const double* b, const double* c) {
+  template<int I>
+  TIT_HD static double tri_piece(const Params& P, bool anti, double eta, const double* a, const double* b, const double* c) {
     const double cut = KG::cutoff(I);
     if (eta >= cut) return 0.0;
     const double radius_sqr = cut * cut - eta * eta;
-    double sector;
-    if constexpr (Anti) sector = KG::template tri_antigrad_sector<I>(eta);
-    else sector = KG::template tri_flux_sector<I>(eta);
-    return tri_edge<Anti, I>(P, eta, radius_sqr, sector, a, b) + tri_edge<Anti, I>(P, eta, radius_sqr, sector, b, c) + tri_edge<Anti, I>(P, eta, radius_sqr, sector, c, a);
+    const double sector = anti ? KG::template tri_antigrad_sector<I>(eta) : KG::template tri_flux_sector<I>(eta);
+    double result = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+      const double* p0 = k == 0 ? a : k == 1 ? b : c;
+      const double* p1 = k == 0 ? b : k == 1 ? c : a;
+      result += tri_edge<I>(P.tiny, anti, eta, radius_sqr, sector, p0[0], p0[1], p1[0], p1[1]);
+    }
+    return result;
   }
-  template<bool Anti, int I = 0>
-  TIT_HD static double tri_integral(const Params& P, double eta, const double* a, const double* b, const double* c) {
+  template<int I = 0>
+  TIT_HD static double tri_integral(const Params& P, bool anti, double eta, const double* a, const double* b, const double* c) {
     if constexpr (I >= KG::num_pieces) return 0.0;
-    else return tri_piece<Anti, I>(P, eta, a, b, c) + tri_integral<Anti, I + 1>(P, eta, a, b, c);
+    else return tri_piece<I>(P, anti, eta, a, b, c) + tri_integral<I + 1>(P, anti, eta, a, b, c);
   }
 
   // Scalar flux magnitude along the face normal: grad gamma_as = n * flux_n
@@ -153,7 +171,7 @@ struct SphKernel {
     const double d = -(ax * f.n[0] + ay * f.n[1]) * P.hinv;
     const double z_min = (ax * f.e[0] + ay * f.e[1]) * P.hinv;
     const double z_max = z_min + f.len * P.hinv;
-    const double u = seg_integral<Anti>(P, fabs(d), z_min, z_max);
+    const double u = seg_integral(P, Anti, fabs(d), z_min, z_max);
     if constexpr (Anti) return copysign(P.w_anti, d) * u;
     else return P.w_flux * u;
   }
@@ -168,7 +186,7 @@ struct SphKernel {
     pb[1] = pa[1];
     pc[0] = pa[0] + f.cx * P.hinv;
     pc[1] = pa[1] + f.cy * P.hinv;
-    const double u = tri_integral<Anti>(P, fabs(d), pa, pb, pc);
+    const double u = tri_integral(P, Anti, fabs(d), pa, pb, pc);
     if constexpr (Anti) return copysign(P.w_anti, d) * u;
     else return P.w_flux * u;
   }
