@@ -193,6 +193,15 @@ double orc_kernel_antigrad_flux(int kid, int dim, const double* face, const doub
   });
 }
 
+// Batched variants (n points, packed) so that the quadrature-based known-answer
+// tests of sph/kernel.test.cpp can be restated without per-point call overhead.
+void orc_kernel_value_n(int kid, int dim, const double* x, size_t n, double h, double* out) {
+  for (size_t i = 0; i < n; ++i) out[i] = orc_kernel_value(kid, dim, x + i * dim, h);
+}
+void orc_kernel_antigrad_n(int kid, int dim, const double* x, size_t n, double h, double* out) {
+  for (size_t i = 0; i < n; ++i) orc_kernel_antigrad(kid, dim, x + i * dim, h, out + i * dim);
+}
+
 // ---- geometry layer ----------------------------------------------------------
 void orc_segment_clamp(const double* seg, const double* p, double* out) { st<2>(out, Segment{ld<2>(seg), ld<2>(seg + 2)}.clamp(ld<2>(p))); }
 void orc_triangle_clamp(const double* tri, const double* p, double* out) { st<3>(out, Triangle{ld<3>(tri), ld<3>(tri + 3), ld<3>(tri + 6)}.clamp(ld<3>(p))); }

@@ -66,6 +66,8 @@ def load(fast: bool = False) -> C.CDLL:
     lib.orc_kernel_width_deriv.restype = d
     lib.orc_kernel_width_deriv.argtypes = [C.c_int, C.c_int, dp, d]
     lib.orc_kernel_antigrad.argtypes = [C.c_int, C.c_int, dp, d, dp]
+    lib.orc_kernel_value_n.argtypes = [C.c_int, C.c_int, dp, sz, d, dp]
+    lib.orc_kernel_antigrad_n.argtypes = [C.c_int, C.c_int, dp, sz, d, dp]
     lib.orc_kernel_flux.argtypes = [C.c_int, C.c_int, dp, dp, d, dp]
     lib.orc_kernel_antigrad_flux.restype = d
     lib.orc_kernel_antigrad_flux.argtypes = [C.c_int, C.c_int, dp, dp, d]
