@@ -88,6 +88,19 @@ TITGPU_API int titgpu_rhs_only(titgpu_ctx* ctx);
  * fields reflect the last step. */
 TITGPU_API int titgpu_step(titgpu_ctx* ctx, int nsteps, double* dt_last);
 
+/* Which derived fields titgpu_step publishes for titgpu_download after the LAST
+ * step of a call. The reference recomputes all 17 varying fields of every
+ * particle in every step (fluid_equations.hpp:331-512) although its time loop
+ * reads them only when it writes an output frame (wcsph.cpp:186-189); on the
+ * GPU publishing is optional:
+ *   2 (default)  every field of every particle, as the reference;
+ *   1            derived fields of fluid particles only (the shifting sums N, L,
+ *                grad_v, grad_rho of wall particles are never read by the step);
+ *   0            state only (r, v, rho, m); derived fields keep their last
+ *                published values.
+ * The state evolution is identical at every level. */
+TITGPU_API int titgpu_set_outputs(titgpu_ctx* ctx, int level);
+
 /* ParticleMesh adjacency (particle_mesh.hpp:67-72, 137-147): CSR, rows in
  * original particle order, columns ascending, self included. Call with
  * cols == NULL to obtain nnz. */

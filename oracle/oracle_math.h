@@ -207,11 +207,17 @@ template<int D> struct Grid {
     const Vec<D> half = ext / 2.0;
     BBox<D> s = search;
     s.grow(half).intersect(box).shrink(half);
+    // The reference requires a non-empty intersection (grid.hpp:160) and has no
+    // emptiness test. A search box that is truly disjoint from the grid box ends
+    // up with lo - hi >= half a cell here; anything less is an overlap whose
+    // lo/hi may cross by rounding only (e.g. a wall face lying exactly on the
+    // upper side of the grid box) and must NOT be dropped.
     for (int i = 0; i < D; ++i)
-      if (!(s.lo[i] <= s.hi[i])) return false;
+      if (!(s.lo[i] - s.hi[i] <= half[i] * (1.0 - 1e-9))) return false;
+    for (int i = 0; i < D; ++i) { s.lo[i] = std::max(s.lo[i], box.lo[i]); s.hi[i] = std::max(s.hi[i], box.lo[i]); }
     lo = cell_index(s.lo);
     hi = cell_index(s.hi);
-    for (int i = 0; i < D; ++i) { lo[i] = std::min(lo[i], num[i] - 1); hi[i] = std::min(hi[i], num[i] - 1); }
+    for (int i = 0; i < D; ++i) { lo[i] = std::min(lo[i], num[i] - 1); hi[i] = std::max(std::min(hi[i], num[i] - 1), lo[i]); }
     return true;
   }
 };

@@ -181,6 +181,34 @@ def test_one_step_parity_3d(oracle):
     check_step(oracle, case_3d())
 
 
+def test_output_levels_do_not_change_the_state(oracle):
+    """titgpu_set_outputs: publishing derived fields is optional, the state evolution is not."""
+    case = cases.dam_break_2d(16)
+    ref = None
+    for level in (2, 1, 0):
+        g = tb.Solver(2)
+        tb.load_case(g, case)
+        g.set_outputs(level)
+        g.initialize()
+        g.step(3)
+        st = [g.download(f) for f in STEP_FIELDS]
+        if ref is None:
+            ref = st
+            N2 = g.download("N")
+            assert np.abs(N2[case.n_fluid:]).max() > 0  # wall-particle sums are published at level 2
+        else:
+            for a, b in zip(st, ref):
+                assert np.array_equal(a, b)
+        if level == 1:
+            N1 = g.download("N")
+            assert np.array_equal(N1[: case.n_fluid], N2[: case.n_fluid])
+            assert np.abs(N1[case.n_fluid:]).max() == 0
+        if level == 0:
+            assert np.abs(g.download("N")).max() == 0
+    with pytest.raises(tb.TitGpuError):
+        g.set_outputs(3)
+
+
 def test_strided_upload_download(oracle):
     """The reference pads Vec<double,3> to 32 bytes."""
     case = cases.dam_break_3d(4)

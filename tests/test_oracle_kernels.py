@@ -136,7 +136,10 @@ def antigrad_n(kid, pts, h):
 
 
 def approx(a, b, eps=TINY):
-    return np.all(np.abs(np.asarray(a, float) - np.asarray(b, float)) <= eps)
+    """approx_equal_to: |a - b| <= tiny for scalars (core/math.hpp:156-162), Euclidean
+    norm for vectors (core/_vec/vec.hpp:681-687)."""
+    d = np.atleast_1d(np.asarray(a, float) - np.asarray(b, float))
+    return float(np.dot(d, d)) <= eps * eps
 
 
 # ---- the oracle's constants and radial functions against the exact definitions
@@ -235,15 +238,21 @@ def test_antigrad_divergence_identity(kid, h, dim):
 
 
 # ---- face geometry helpers (geom/segment.hpp:61-68, geom/triangle.hpp:78-100)
+def normalize(v):
+    """core/_vec/vec.hpp:663-678: vectors shorter than tiny normalise to ZERO. The
+    reference's flux tests rely on it: the h/6 triangle at h = 0.01 has
+    |wnormal| = 2.4e-6 < tiny, so both flux() and the estimate are exactly 0."""
+    n2 = float(np.dot(v, v))
+    return v / np.sqrt(n2) if n2 >= TINY * TINY else np.zeros_like(v)
+
+
 def seg_normal(a, b):
-    ba = np.asarray(b) - np.asarray(a)
-    n = np.array([ba[1], -ba[0]])
-    return n / np.linalg.norm(n)
+    ba = np.asarray(b, float) - np.asarray(a, float)
+    return normalize(np.array([ba[1], -ba[0]]))
 
 
 def tri_normal(a, b, c):
-    n = np.cross(np.asarray(b) - a, np.asarray(c) - a)
-    return n / np.linalg.norm(n)
+    return normalize(np.cross(np.asarray(b, float) - a, np.asarray(c, float) - a) / 2)
 
 
 def flux_estimate_2d(kid, seg, x, h):

@@ -18,7 +18,8 @@ import numpy as np
 from . import cases  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtitgpu.so")
+# TITGPU_LIB selects a tuning variant of the SAME CUDA library (see build.py); there is no other backend.
+LIB_PATH = os.environ.get("TITGPU_LIB") or os.path.join(_HERE, "libtitgpu.so")
 
 FIELDS = {
     "m": 0, "gamma": 0, "rho": 0, "drho_dt": 0, "p": 0, "cs": 0, "phi": 0, "rho_raw": 0,
@@ -29,7 +30,7 @@ FIELDS = {
 ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
-    "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
+    "titgpu_set_outputs", "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
     "titgpu_profile_enable", "titgpu_profile_reset", "titgpu_profile_count", "titgpu_profile_get", "titgpu_measure_fp64_peak",
 ]
 
@@ -63,6 +64,7 @@ def load_library() -> C.CDLL:
         getattr(lib, f).argtypes = [vp]
     lib.titgpu_step.argtypes = [vp, C.c_int, C.POINTER(d)]
     lib.titgpu_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
+    lib.titgpu_set_outputs.argtypes = [vp, C.c_int]
     lib.titgpu_launch_count.argtypes = [vp]
     lib.titgpu_launch_count.restype = C.c_ulonglong
     lib.titgpu_stream.argtypes = [vp]
@@ -166,6 +168,10 @@ class Solver:
         dt = C.c_double(0)
         self._ck(self.lib.titgpu_step(self.h, nsteps, C.byref(dt)), "titgpu_step")
         return dt.value
+
+    def set_outputs(self, level):
+        """0 state only, 1 + derived fields of fluid particles, 2 everything (reference, default)."""
+        self._ck(self.lib.titgpu_set_outputs(self.h, int(level)), "titgpu_set_outputs")
 
     def neighbors(self):
         nnz = C.c_size_t(0)

@@ -15,8 +15,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libtitgpu.so")
+# TITGPU_VARIANT / TITGPU_DEFINES build a tuning variant next to the product library
+# (libtitgpu_<variant>.so, selected at run time with TITGPU_LIB).
+VARIANT = os.environ.get("TITGPU_VARIANT", "")
+DEFINES = [f"-D{d}" for d in os.environ.get("TITGPU_DEFINES", "").split() if d]
+OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libtitgpu" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-ccbin", "/usr/bin/g++"]
@@ -58,7 +62,7 @@ def build(dims=(2, 3), kernels=(0, 1, 2, 3, 4, 5), jobs=None, verbose=False, ptx
             o = os.path.join(OBJ, f"inst_{d}_{k}.o")
             objs.append(o)
             if _newer(o, [inst] + hdrs) or ptxas_v:
-                tasks.append([NVCC, *ARCH, *FLAGS, *extra, f"-DTIT_D={d}", f"-DTIT_K={k}", "-c", inst, "-o", o])
+                tasks.append([NVCC, *ARCH, *FLAGS, *extra, *DEFINES, f"-DTIT_D={d}", f"-DTIT_K={k}", "-c", inst, "-o", o])
     outs = []
     if tasks:
         with cf.ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 4)) as ex:

@@ -58,6 +58,7 @@ struct Ctx {
   bool sorted_identity = true;  // state order == original order
   size_t nf = 0, nx = 0, n = 0;
   double search_hint = 0, face_hint = 0;
+  int output_level = 2;  // titgpu_set_outputs: 0 state only, 1 + derived fields of fluid particles, 2 all (reference)
 
   // Packed particle records in sorted order (see engine.cuh): A = position +
   // density (+ mass in 2-D), B = velocity (+ mass in 3-D); A0 / B0 = the state

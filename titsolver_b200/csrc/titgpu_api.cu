@@ -283,6 +283,13 @@ int titgpu_step(titgpu_ctx* h, int nsteps, double* dt_last) {
   if (dt_last) *dt_last = dt;
   TITGPU_LEAVE()
 }
+int titgpu_set_outputs(titgpu_ctx* h, int level) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (level < 0 || level > 2) return fail(c, "output level must be 0, 1 or 2");
+  c.output_level = level;
+  return 0;
+}
 int titgpu_neighbors(titgpu_ctx* h, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz) {
   TITGPU_ENTER(true)
   if (!nnz) return fail(c, "nnz must not be null");
