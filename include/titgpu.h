@@ -106,6 +106,45 @@ TITGPU_API int titgpu_set_outputs(titgpu_ctx* ctx, int level);
  * cols == NULL to obtain nnz. */
 TITGPU_API int titgpu_neighbors(titgpu_ctx* ctx, uint64_t* row_offsets, uint64_t* cols, size_t cap, size_t* nnz);
 
+/* ---- Slab domain decomposition (one context per GPU / rank) -------------------
+ * Replaces, across GPUs, what the reference's block partition does across
+ * threads (sph/particle_mesh.hpp:165-241; geom/partition/): every rank owns
+ * the fluid particles of one slab plus GHOST copies of the neighbouring slabs'
+ * particles within a halo, refreshed before every neighbour search. Ghosts are
+ * neighbours only: their right-hand sides are not evaluated, their records
+ * are replaced by the next exchange. The rank-local wall particles / faces are
+ * those of the slab plus halo and never move. The host side (which particles
+ * to send where, NCCL send/recv) lives above this ABI: titsolver_b200/slab.py.
+ *
+ * Fluid records cross this part of the ABI as DEVICE arrays of 4 doubles per
+ * particle in rank-local order (owned particles first, then ghosts):
+ *   3-D: A = {x, y, z, rho}  B = {vx, vy, vz, m}
+ *   2-D: A = {x, y, rho, m}  B = {vx, vy, 0, 0}
+ * A0 / B0 = the same at the beginning of the step (SSPRK u_old); may be NULL. */
+
+/* Capacity for the fluid particles of this rank (owned + ghosts); call before
+ * the first titgpu_upload. */
+TITGPU_API int titgpu_mg_reserve(titgpu_ctx* ctx, size_t max_fluid);
+/* Current numbers of owned, ghost and wall particles. */
+TITGPU_API int titgpu_mg_counts(titgpu_ctx* ctx, size_t* n_owned, size_t* n_ghost, size_t* n_fixed);
+/* Copy the fluid records (owned + ghosts, rank-local order) into caller buffers. */
+TITGPU_API int titgpu_mg_export(titgpu_ctx* ctx, double* A_dev, double* B_dev, double* A0_dev, double* B0_dev);
+/* Replace the fluid particles of the context by n_owned owned + n_ghost ghost
+ * records (the wall particles stay). Asynchronous on the context's stream. */
+TITGPU_API int titgpu_mg_import(titgpu_ctx* ctx, size_t n_owned, size_t n_ghost, const double* A_dev, const double* B_dev, const double* A0_dev, const double* B0_dev);
+/* titgpu_step calls `fn(user, phase)` wherever the ranks must talk; a non-zero
+ * return aborts the step. phase 0: before the first neighbour search of a step
+ * (particles may change owner); 1: before the later searches of the right-hand
+ * sides; 3: before the search of post_integrate (wider halo: the shifting /
+ * free-surface passes read neighbours of neighbours); 2: reduce the time-step
+ * scalars over the ranks — titgpu_mg_scalars()[2] with MIN, [1] with MAX
+ * (both non-negative doubles; fluid_equations.hpp:203-221). The callback may
+ * call titgpu_mg_export / titgpu_mg_import / titgpu_mg_counts on the context. */
+typedef int (*titgpu_exchange_fn)(void* user, int phase);
+TITGPU_API int titgpu_mg_set_exchange(titgpu_ctx* ctx, titgpu_exchange_fn fn, void* user);
+/* Device pointer to the step scalars {dt, max |dv_dt|^2, min dt candidate}. */
+TITGPU_API void* titgpu_mg_scalars(titgpu_ctx* ctx);
+
 /* Block until all queued work of the context has finished. */
 TITGPU_API int titgpu_synchronize(titgpu_ctx* ctx);
 /* Number of CUDA kernels this context has launched so far. */

@@ -30,7 +30,8 @@ FIELDS = {
 ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
-    "titgpu_set_outputs", "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
+    "titgpu_set_outputs", "titgpu_mg_reserve", "titgpu_mg_counts", "titgpu_mg_export", "titgpu_mg_import", "titgpu_mg_set_exchange", "titgpu_mg_scalars",
+    "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
     "titgpu_profile_enable", "titgpu_profile_reset", "titgpu_profile_count", "titgpu_profile_get", "titgpu_measure_fp64_peak",
 ]
 
@@ -40,6 +41,9 @@ class TitGpuError(RuntimeError):
 
 
 _lib = None
+
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
 
 
 def load_library() -> C.CDLL:
@@ -65,6 +69,13 @@ def load_library() -> C.CDLL:
     lib.titgpu_step.argtypes = [vp, C.c_int, C.POINTER(d)]
     lib.titgpu_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
     lib.titgpu_set_outputs.argtypes = [vp, C.c_int]
+    lib.titgpu_mg_reserve.argtypes = [vp, sz]
+    lib.titgpu_mg_counts.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    lib.titgpu_mg_export.argtypes = [vp, vp, vp, vp, vp]
+    lib.titgpu_mg_import.argtypes = [vp, sz, sz, vp, vp, vp, vp]
+    lib.titgpu_mg_set_exchange.argtypes = [vp, EXCHANGE_FN, vp]
+    lib.titgpu_mg_scalars.argtypes = [vp]
+    lib.titgpu_mg_scalars.restype = vp
     lib.titgpu_launch_count.argtypes = [vp]
     lib.titgpu_launch_count.restype = C.c_ulonglong
     lib.titgpu_stream.argtypes = [vp]
@@ -172,6 +183,31 @@ class Solver:
     def set_outputs(self, level):
         """0 state only, 1 + derived fields of fluid particles, 2 everything (reference, default)."""
         self._ck(self.lib.titgpu_set_outputs(self.h, int(level)), "titgpu_set_outputs")
+
+    # ---- slab decomposition (see slab.py) ----
+    def mg_reserve(self, max_fluid):
+        self._ck(self.lib.titgpu_mg_reserve(self.h, int(max_fluid)), "titgpu_mg_reserve")
+
+    def mg_counts(self):
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._ck(self.lib.titgpu_mg_counts(self.h, C.byref(a), C.byref(b), C.byref(c)), "titgpu_mg_counts")
+        return a.value, b.value, c.value
+
+    def mg_export(self, A_ptr, B_ptr, A0_ptr=None, B0_ptr=None):
+        self._ck(self.lib.titgpu_mg_export(self.h, A_ptr, B_ptr, A0_ptr, B0_ptr), "titgpu_mg_export")
+
+    def mg_import(self, n_owned, n_ghost, A_ptr, B_ptr, A0_ptr=None, B0_ptr=None):
+        self._ck(self.lib.titgpu_mg_import(self.h, int(n_owned), int(n_ghost), A_ptr, B_ptr, A0_ptr, B0_ptr), "titgpu_mg_import")
+        self.n_fluid = int(n_owned) + int(n_ghost)
+
+    def mg_set_exchange(self, fn):
+        """`fn(phase) -> int`; kept alive by the solver."""
+        self._exchange_cb = EXCHANGE_FN(lambda user, phase: int(fn(phase))) if fn is not None else EXCHANGE_FN(0)
+        self._ck(self.lib.titgpu_mg_set_exchange(self.h, self._exchange_cb, None), "titgpu_mg_set_exchange")
+
+    @property
+    def mg_scalars(self):
+        return self.lib.titgpu_mg_scalars(self.h)
 
     def neighbors(self):
         nnz = C.c_size_t(0)

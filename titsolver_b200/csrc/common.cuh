@@ -167,6 +167,7 @@ struct Params {
   double cos_fov2;  // cos(pi/4)^2 as evaluated in double (fluid_equations.hpp:406-407)
   int eos;
   int nf, nx, n;
+  int n_owned;    // slab decomposition: fluid particles [n_owned, nf) are ghosts (neighbours only); == nf otherwise
   float pre_thr;  // FP32 pre-filter threshold on the squared distance in cell units
   float oor;      // |grid coordinate| beyond which the FP32 pre-filter is bypassed
   GridDesc grid;   // particle hash

@@ -58,6 +58,11 @@ struct Ctx {
   bool sorted_identity = true;  // state order == original order
   size_t nf = 0, nx = 0, n = 0;
   double search_hint = 0, face_hint = 0;
+  // Slab decomposition (titgpu_mg_*): capacity reserved for a varying number of
+  // fluid particles, and the callback the step invokes where ranks must talk.
+  size_t reserve_fluid = 0, cap_n = 0;
+  int (*exchange_fn)(void*, int) = nullptr;
+  void* exchange_user = nullptr;
   int output_level = 2;  // titgpu_set_outputs: 0 state only, 1 + derived fields of fluid particles, 2 all (reference)
 
   // Packed particle records in sorted order (see engine.cuh): A = position +
@@ -157,6 +162,8 @@ struct EngineVTable {
   int (*neighbors)(Ctx&, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz);
   int (*download_state)(Ctx&, int field, double* dst_dev);  // unsort into original order
   int (*upload_state)(Ctx&, int field, const double* src_dev);
+  int (*mg_export)(Ctx&, double* A_dev, double* B_dev, double* A0_dev, double* B0_dev);
+  int (*mg_import)(Ctx&, size_t n_owned, size_t n_ghost, const double* A_dev, const double* B_dev, const double* A0_dev, const double* B0_dev);
 };
 
 const EngineVTable* get_engine(int dim, int kernel_id);

@@ -33,7 +33,10 @@ int fail(Ctx& c, const std::string& msg) {
 }
 
 int alloc_particles(Ctx& c) {
-  const size_t n = std::max<size_t>(c.n, 1), D = size_t(c.dim);
+  // Buffers are sized for the reserved capacity (slab decomposition: the number
+  // of fluid particles of a rank varies from exchange to exchange).
+  c.cap_n = std::max<size_t>(std::max(c.nf, c.reserve_fluid) + c.nx, 1);
+  const size_t n = c.cap_n, D = size_t(c.dim);
   for (DBuf& b : c.bufA) TIT_CUDA_OK(c, b.ensure(n * sizeof(double4)));
   for (DBuf& b : c.bufB) TIT_CUDA_OK(c, b.ensure(n * sizeof(double4)));
   for (DBuf& b : c.buf_orig) TIT_CUDA_OK(c, b.ensure(n * 4));
@@ -72,7 +75,7 @@ int alloc_particles(Ctx& c) {
   c.grid_ready = false;
   c.fixed_cache_valid = false;
   c.sized = true;
-  c.prm.nf = int(c.nf); c.prm.nx = int(c.nx); c.prm.n = int(c.n);
+  c.prm.nf = int(c.nf); c.prm.nx = int(c.nx); c.prm.n = int(c.n); c.prm.n_owned = int(c.nf);
   return 0;
 }
 
@@ -90,7 +93,7 @@ void pack_out(const std::vector<double>& in, size_t n, int width, size_t stride,
 int check_ready(Ctx& c, bool need_particles) {
   if (!c.params_set) return fail(c, "titgpu_set_params has not been called");
   if (need_particles && !c.sized) return fail(c, "no particles uploaded");
-  if (need_particles && c.n > 0x7fffffffull / 16) return fail(c, "too many particles for 32-bit indexing");
+  if (need_particles && c.cap_n > 0x7fffffffull / 16) return fail(c, "too many particles for 32-bit indexing");
   return 0;
 }
 
@@ -187,7 +190,7 @@ int titgpu_upload(titgpu_ctx* h, size_t n_fluid, size_t n_fixed, const char* fie
   if (f < 0) return fail(c, std::string("unknown field '") + field + "'");
   if (!c.sized || n_fluid != c.nf || n_fixed != c.nx) {
     c.nf = n_fluid; c.nx = n_fixed; c.n = n_fluid + n_fixed;
-    if (c.n > 0x7fffffffull / 16) return fail(c, "too many particles for 32-bit indexing");
+    if (std::max(c.nf, c.reserve_fluid) + c.nx > 0x7fffffffull / 16) return fail(c, "too many particles for 32-bit indexing");
     if (alloc_particles(c)) return 1;
   }
   if (c.n == 0) return 0;
@@ -290,6 +293,45 @@ int titgpu_set_outputs(titgpu_ctx* h, int level) {
   c.output_level = level;
   return 0;
 }
+// ---- slab decomposition --------------------------------------------------------
+int titgpu_mg_reserve(titgpu_ctx* h, size_t max_fluid) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (c.sized && max_fluid + c.nx > c.cap_n) return fail(c, "titgpu_mg_reserve must precede the first upload");
+  c.reserve_fluid = max_fluid;
+  return 0;
+}
+int titgpu_mg_set_exchange(titgpu_ctx* h, titgpu_exchange_fn fn, void* user) {
+  if (!h) return 1;
+  h->c.exchange_fn = fn;
+  h->c.exchange_user = user;
+  return 0;
+}
+int titgpu_mg_counts(titgpu_ctx* h, size_t* n_owned, size_t* n_ghost, size_t* n_fixed) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (n_owned) *n_owned = size_t(c.prm.n_owned);
+  if (n_ghost) *n_ghost = c.nf - size_t(c.prm.n_owned);
+  if (n_fixed) *n_fixed = c.nx;
+  return 0;
+}
+int titgpu_mg_export(titgpu_ctx* h, double* A_dev, double* B_dev, double* A0_dev, double* B0_dev) {
+  TITGPU_ENTER(true)
+  if (!A_dev || !B_dev || (!A0_dev) != (!B0_dev)) return fail(c, "titgpu_mg_export: bad buffers");
+  if (c.vt->mg_export(c, A_dev, B_dev, A0_dev, B0_dev)) return 1;
+  TIT_CUDA_OK(c, cudaGetLastError());
+  return 0;
+}
+int titgpu_mg_import(titgpu_ctx* h, size_t n_owned, size_t n_ghost, const double* A_dev, const double* B_dev, const double* A0_dev, const double* B0_dev) {
+  TITGPU_ENTER(true)
+  if ((n_owned + n_ghost) && (!A_dev || !B_dev)) return fail(c, "titgpu_mg_import: bad buffers");
+  if ((!A0_dev) != (!B0_dev)) return fail(c, "titgpu_mg_import: bad buffers");
+  if (c.vt->mg_import(c, n_owned, n_ghost, A_dev, B_dev, A0_dev, B0_dev)) return 1;
+  TIT_CUDA_OK(c, cudaGetLastError());
+  return 0;
+}
+void* titgpu_mg_scalars(titgpu_ctx* h) { return h ? h->c.scalars.p : nullptr; }
+
 int titgpu_neighbors(titgpu_ctx* h, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz) {
   TITGPU_ENTER(true)
   if (!nnz) return fail(c, "nnz must not be null");
