@@ -206,11 +206,26 @@ def run_ours(args, rank, local_rank, world):
     w = WORKLOADS[args.workload]
     dim = w["dim"]
     n_col = args.n_col or w["n_col"]
-    case = make_case(dim, n_col)
-    n = case.n
+    slab = None
+    if world > 1:
+        # Weak scaling: the 3-D tank is made `world` times deeper along z and cut into
+        # `world` slabs (one per GPU) with ghost layers exchanged over NCCL send/recv
+        # before every neighbour search (titsolver_b200/slab.py).
+        if dim != 3:
+            raise SystemExit("bench.py: the multi-GPU workload is the 3-D dam break (use --workload c3/c4/c5)")
+        from titsolver_b200 import cases
+        from titsolver_b200.slab import SlabSolver
 
-    solver = tb.Solver(dim, device=local_rank)
-    tb.load_case(solver, case)
+        case, edges = cases.dam_break_3d_slab(n_col, world, rank)
+        slab = SlabSolver(case, rank, world, axis=2, edges=edges, device=local_rank, local=True)
+        solver = slab.solver
+        n_global = case.meta["n_fluid_global"] + case.meta["n_fixed_global"]
+        n = n_global / world  # particles per GPU (wall particles of the halos are not counted twice)
+    else:
+        case = make_case(dim, n_col)
+        n = case.n
+        solver = tb.Solver(dim, device=local_rank)
+        tb.load_case(solver, case)
     solver.initialize()
     stream = torch.cuda.ExternalStream(solver.stream, device=torch.device("cuda", local_rank))
 
@@ -246,17 +261,51 @@ def run_ours(args, rank, local_rank, world):
     value = world * n * args.steps / (ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI every step -----------------
-    host = {f: torch.empty(solver._shape(f), dtype=torch.float64).pin_memory() for f in ("r", "v", "rho")}
-    for f in host:
-        solver.download_raw(f, host[f].data_ptr())
-    h2d = d2h = sum(h.numel() * 8 for h in host.values())
-
-    def e2e_step():
-        for f in ("r", "v", "rho"):
-            solver.upload_raw(f, host[f].data_ptr())
-        solver.step(1)
-        for f in ("r", "v", "rho"):
+    if slab is None:
+        host = {f: torch.empty(solver._shape(f), dtype=torch.float64).pin_memory() for f in ("r", "v", "rho")}
+        for f in host:
             solver.download_raw(f, host[f].data_ptr())
+        h2d = d2h = sum(h.numel() * 8 for h in host.values())
+
+        def e2e_step():
+            for f in ("r", "v", "rho"):
+                solver.upload_raw(f, host[f].data_ptr())
+            solver.step(1)
+            for f in ("r", "v", "rho"):
+                solver.download_raw(f, host[f].data_ptr())
+    else:
+        # Slab mode: the owned fluid records (r, rho | v, m: 64 B per particle) travel
+        # host -> device before and device -> host after every step.
+        cap = int(slab.solver.mg_counts()[0] * 1.05) + 4096
+        hostA = torch.empty((cap, 4), dtype=torch.float64).pin_memory()
+        hostB = torch.empty((cap, 4), dtype=torch.float64).pin_memory()
+        tdev = torch.device("cuda", local_rank)
+        state = {"n": 0}
+
+        def pull():
+            with torch.cuda.stream(stream):
+                rec, n_owned = slab._export(False)
+                hostA[:n_owned].copy_(rec[:n_owned, 0:4], non_blocking=True)
+                hostB[:n_owned].copy_(rec[:n_owned, 4:8], non_blocking=True)
+            solver.synchronize()
+            state["n"] = n_owned
+
+        def push():
+            k = state["n"]
+            with torch.cuda.stream(stream):
+                dA = hostA[:k].to(tdev, non_blocking=True)
+                dB = hostB[:k].to(tdev, non_blocking=True)
+                solver.mg_import(k, 0, dA.data_ptr(), dB.data_ptr())
+                slab.gid = slab.gid[:k]
+                slab._keep = [dA, dB]
+
+        pull()
+        h2d = d2h = int(state["n"]) * 64
+
+        def e2e_step():
+            push()
+            solver.step(1)
+            pull()
 
     # Between output frames the reference's time loop reads nothing but what the
     # next step needs (wcsph.cpp:170-193): the e2e loop publishes the state only.
@@ -290,7 +339,7 @@ def run_ours(args, rank, local_rank, world):
         cnt, tot = prof[rhs_name]
         avg_s = tot / cnt * 1e-3
         ach = alg_bytes_rhs(dim) * n / avg_s / 1e9
-        flops = alg_flops_rhs(dim) * case.n_fluid / avg_s / 1e12
+        flops = alg_flops_rhs(dim) * (case.n_fluid if slab is None else case.meta["n_fluid_global"] / world) / avg_s / 1e12
         roof = {
             "bound": "hbm", "kernel": rhs_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
             "peak_source": peak_src, "alg_bytes_per_particle": alg_bytes_rhs(dim), "launches": cnt, "avg_ms": avg_s * 1e3,
@@ -309,10 +358,10 @@ def run_ours(args, rank, local_rank, world):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"] if not args.n_col else f"{dim}D dam break, n_col={n_col}", "particles_per_gpu": n, "n_fluid": case.n_fluid, "n_fixed": case.n_fixed,
-                   "integrator": "ssprk3", "kernel": "SixthOrderWendland", "eos": "tait", "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (slab decomposition not in this round)",
+        "config": {"workload": (w["label"] if not args.n_col else f"{dim}D dam break, n_col={n_col}") + ("" if world == 1 else f", per GPU; {world} GPUs weak-scaled along z"), "particles_per_gpu": int(n), "n_fluid": case.n_fluid if slab is None else case.meta["n_fluid_global"], "n_fixed": case.n_fixed if slab is None else case.meta["n_fixed_global"],
+                   "integrator": "ssprk3", "kernel": "SixthOrderWendland", "eos": "tait", "parallelism": "single GPU" if world == 1 else f"{world} slabs along z (tank {world}x deeper), one rank per GPU, ghost-layer exchange over NCCL send/recv before every neighbour search, dt all-reduce per step",
                    "outputs": "value: all 17 fields of all particles published after the last timed step (reference semantics); e2e: state only (r, v, rho) every step",
-                   "l2_policy": "inputs larger than L2 (state arrays of %d MB)" % (n * (2 * dim + 2) * 8 // 2**20)},
+                   "l2_policy": "inputs larger than L2 (state arrays of %d MB)" % (int(n) * (2 * dim + 2) * 8 // 2**20)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),

@@ -107,17 +107,26 @@ def dam_break_2d(n_col: int = 80, H: float = 0.6) -> Case:
                 {"name": f"dam_break_2d_{WM}x{WN}", "tank": (PW, PH)})
 
 
-def _box_wall_mesh(ext, n_cells, inward=True):
+def _box_wall_mesh(ext, n_cells, inward=True, cell_range=None):
     """Structured triangulation of the 6 walls of [0,ext]; two right triangles per
     quad; vertices shared along edges. Triangle normals (cross(ba, ca)) point
     into the box when `inward`. Vectorised: the 10 M-particle case has 1.8 M
-    wall vertices."""
+    wall vertices. `cell_range = (axis, c0, c1)` keeps only the quads whose cell
+    index along `axis` lies in [c0, c1) (and the end walls normal to `axis` only
+    if the range reaches them): the part of the mesh one slab of a domain
+    decomposition needs, with coordinates identical to the full mesh."""
     n = np.asarray(n_cells, dtype=np.int64)
     tris = []  # (nt, 3, 3) integer lattice coordinates of the triangle corners
+    r_axis, c0, c1 = cell_range if cell_range is not None else (-1, 0, 0)
+
+    def rng(a):
+        return np.arange(max(c0, 0), min(c1, n[a])) if a == r_axis else np.arange(n[a])
 
     def wall(axis, level, u_axis, v_axis, flip):
+        if axis == r_axis and not ((level == 0 and c0 <= 0) or (level == n[axis] and c1 >= n[axis])):
+            return
         # Quad corners p00 -> p10 (+u) -> p11 -> p01 (+v); normal = e_u x e_v.
-        iu, iv = np.meshgrid(np.arange(n[u_axis]), np.arange(n[v_axis]), indexing="ij")
+        iu, iv = np.meshgrid(rng(u_axis), rng(v_axis), indexing="ij")
         iu, iv = iu.ravel(), iv.ravel()
 
         def P(du, dv):
@@ -142,6 +151,8 @@ def _box_wall_mesh(ext, n_cells, inward=True):
     wall(1, n[1], 2, 0, inward)
     wall(0, 0, 1, 2, not inward)      # x = 0, normal +x (e_y x e_z)
     wall(0, n[0], 1, 2, inward)
+    if not tris:
+        return np.zeros((0, 3)), np.zeros((0, 3), np.uint64)
     t = np.concatenate(tris, axis=0)
     key = (t[..., 0] * (n[1] + 1) + t[..., 1]) * (n[2] + 1) + t[..., 2]
     ukey, inv = np.unique(key.ravel(), return_inverse=True)
@@ -200,3 +211,51 @@ def dam_break_3d(n_col: int = 16, H: float = 0.6, wall_ratio: float = 1.0, tank=
     rho[:nf] = rho0 + rho0 * g * (H - rf[:, 1]) / cs0**2
     return Case(3, nf, nx, r, m, rho, verts, faces, cverts, cfaces, g, mu, cs0, rho0, 7.0, h0, dr, H,
                 {"name": f"dam_break_3d_{WM}x{WN}x{WK}", "tank": ext, "wall_ratio": wall_ratio, "jitter": jitter})
+
+
+def dam_break_3d_slab(n_col: int, world: int, rank: int, H: float = 0.6, tank=(5.366, 4.0, 1.0), halo_cells: int = 26):
+    """Rank-local part of the weak-scaling 3-D dam break: the tank of
+    `dam_break_3d` made `world` times deeper along z (the flow is z-invariant, so
+    the slabs stay balanced for the whole run), cut into `world` slabs along z.
+
+    Returns (case, edges): `case` holds the fluid particles this rank owns
+    (`case.meta["gid"]` = their global lattice indices), the wall vertices /
+    faces within `halo_cells` wall cells of the slab (fixed particles = those
+    vertices) and the global containment box. Coordinates are bit-identical to
+    those of the global case `dam_break_3d(n_col, tank=(.., .., world * tank_z))`.
+    """
+    dr = H / float(n_col)
+    g, rho0 = 9.81, 1000.0
+    cs0 = 20 * math.sqrt(g * H)
+    h0 = 2.0 * dr
+    m0 = rho0 * dr**3
+    mu = 0.001
+    tz = tank[2] * world
+    ext = (tank[0] * H, tank[1] * H, tz * H)
+    ncell = tuple(max(1, int(math.ceil(e / dr - 1e-9))) for e in ext)
+    WM, WN, WK = 2 * n_col, n_col, int(round(tz * n_col)) - 1
+    per = int(round(tank[2] * n_col))  # lattice planes per slab
+    # slab edges half-way between lattice planes: plane index k (z = dr (k + 1)) belongs to rank (k + 1) // per
+    edges = [-math.inf] + [dr * (per * j - 0.5) for j in range(1, world)] + [math.inf]
+    k0 = max(per * rank - 1, 0) if rank > 0 else 0
+    k1 = per * (rank + 1) - 1 if rank < world - 1 else WK
+    ii, jj, kk = np.meshgrid(np.arange(WM), np.arange(WN), np.arange(k0, k1), indexing="ij")
+    ii, jj, kk = ii.ravel(), jj.ravel(), kk.ravel()
+    rf = dr * np.stack([ii + 1.0, jj + 1.0, kk + 1.0], axis=1)
+    gid = (ii.astype(np.int64) * WN + jj) * WK + kk
+    c0 = (k0 + 1) - halo_cells if rank > 0 else 0
+    c1 = (k1 + 1) + halo_cells if rank < world - 1 else ncell[2]
+    verts, faces = _box_wall_mesh(ext, ncell, inward=True, cell_range=(2, c0, c1))
+    cverts, cfaces = _box_wall_mesh(ext, (1, 1, 1), inward=False)
+    mg = 0.5 * dr
+    cverts = np.where(cverts > 0.0, cverts + mg, cverts - mg)
+    r = np.concatenate([rf, verts], axis=0)
+    nf, nx = rf.shape[0], verts.shape[0]
+    m = np.full(nf + nx, m0)
+    rho = np.full(nf + nx, rho0)
+    rho[:nf] = rho0 + rho0 * g * (H - rf[:, 1]) / cs0**2
+    n_fixed_global = int(np.prod([c + 1 for c in ncell]) - np.prod([c - 1 for c in ncell]))
+    case = Case(3, nf, nx, r, m, rho, verts, faces, cverts, cfaces, g, mu, cs0, rho0, 7.0, h0, dr, H,
+                {"name": f"dam_break_3d_{WM}x{WN}x{WK}_slab{rank}of{world}", "tank": ext, "gid": gid,
+                 "n_fluid_global": WM * WN * WK, "n_fixed_global": n_fixed_global})
+    return case, edges

@@ -190,7 +190,10 @@ class SlabSolver:
 
     MARGIN_DR = 1.0  # extra halo, in particle spacings, for the motion within one step
 
-    def __init__(self, case, rank, world, axis=0, edges=None, device=0, kernel_id=4, eos_id=0, integrator_id=3, group=None, reserve=None, local_case=None):
+    def __init__(self, case, rank, world, axis=0, edges=None, device=0, kernel_id=4, eos_id=0, integrator_id=3, group=None, reserve=None, local=False):
+        """`case` is the GLOBAL case (every rank cuts out its slab; small runs and
+        tests) or, with `local=True`, the rank-local one made by
+        `cases.dam_break_3d_slab` (`edges` required, `case.meta["gid"]` = global ids)."""
         import titsolver_b200 as tb
 
         self.rank, self.world, self.axis = rank, world, axis
@@ -200,12 +203,12 @@ class SlabSolver:
         R = 2.0 * case.h if kernel_id not in (1, 2) else (2.5 if kernel_id == 1 else 3.0) * case.h
         dw = self._max_face_edge(case)
         m = self.MARGIN_DR * case.dr
-        if local_case is None:
+        if not local:
             edges = edges or balanced_edges(case.r[:nf, axis], world)
         self.layout = SlabLayout(axis, edges, 2 * R + dw + m, 4 * R + dw + m)
         lo, hi = self.layout.bounds(rank)
         self.lo, self.hi = lo, hi
-        if local_case is None:
+        if not local:
             x = case.r[:nf, axis]
             own = np.nonzero((x >= lo) & (x < hi))[0]
             wf = self.layout.w_post + R + 2 * dw
@@ -218,9 +221,11 @@ class SlabSolver:
                 w = self.layout.w_post
                 reserve = int(1.3 * np.count_nonzero((x >= lo - w) & (x < hi + w))) + 4096
         else:
-            lverts, lfaces, r, mass, rho, gid = local_case
-            if reserve is None:
-                reserve = 2 * len(gid) + 4096
+            lverts, lfaces, r, mass, rho, gid = case.verts, case.faces, case.r, case.m, case.rho, np.asarray(case.meta["gid"], dtype=np.int64)
+            if reserve is None:  # both halos at the slab's particle density
+                x = case.r[:nf, axis]
+                width = max(float(x.max() - x.min()) + case.dr, case.dr)
+                reserve = int(1.3 * nf * (1.0 + 2.0 * self.layout.w_post / width)) + 4096
         self.n_fixed = len(lverts)
         self.solver = s = tb.Solver(case.dim, kernel_id, eos_id, integrator_id, device=device)
         s.set_params(case.g, case.mu, case.cs0, case.rho0, case.xi, case.h)
