@@ -99,6 +99,34 @@ struct SphKernel {
     if (anti) return KG::template tri_antigrad_line<I>(eta, delta, z, rho, A, L);
     return KG::template tri_flux_line<I>(eta, delta, z, rho, A, L);
   }
+  // line_prim(z_hi) - line_prim(z_lo) on one line from a single pass of the
+  // recurrences (kernels_gen.cuh, *_line_delta) with ONE atan2 and ONE log1p:
+  //   A(z) = atan2(y, x) has x > 0, so A in (-pi/2, pi/2) and
+  //     A1 - A0 = atan2(y1 x0 - x1 y0, x1 x0 + y1 y0) without wrap-around;
+  //   L(z) = asinh(z / beta) = log(w / beta), w = z + rho (z >= 0) or beta^2 / (rho - z),
+  //     L1 - L0 = log1p of a single quotient chosen by the signs of z.
+  // Same value as the difference of two line_prim() up to rounding (~1e-15).
+  template<int I>
+  __device__ __noinline__ static double line_prim_delta(double tiny, bool anti, double eta, double delta, double delta_sqr, double beta_sqr, double beta, double z1, double z0) {
+    const double rho1 = sqrt(fma(z1, z1, beta_sqr)), rho0 = sqrt(fma(z0, z0, beta_sqr));
+    double dA = 0.0, dL = 0.0;
+    if (!(fabs(delta) <= tiny)) {
+      const double y1 = delta * z1 * (rho1 - eta), x1 = fma(delta_sqr, rho1, z1 * z1 * eta);
+      const double y0 = delta * z0 * (rho0 - eta), x0 = fma(delta_sqr, rho0, z0 * z0 * eta);
+      dA = atan2(fma(y1, x0, -(x1 * y0)), fma(x1, x0, y1 * y0));
+    }
+    if (!(fabs(beta) <= tiny)) {
+      double num, den;
+      if (z0 >= 0.0 && z1 >= 0.0) { den = z0 + rho0; num = (z1 - z0) + (rho1 - rho0); }
+      else if (z0 < 0.0 && z1 < 0.0) { den = rho1 - z1; num = (rho0 - rho1) + (z1 - z0); }
+      else if (z1 >= 0.0) { const double prod = (z1 + rho1) * (rho0 - z0); den = beta_sqr; num = prod - beta_sqr; }
+      else { const double prod = (rho1 - z1) * (z0 + rho0); den = prod; num = beta_sqr - prod; }
+      dL = log1p(num / den);
+    }
+    if (anti) return KG::template tri_antigrad_line_delta<I>(eta, delta, z1, rho1, z0, rho0, dA, dL);
+    return KG::template tri_flux_line_delta<I>(eta, delta, z1, rho1, z0, rho0, dA, dL);
+  }
+
   // One edge p0 -> p1 of the projected triangle: the line is cut at its (up to
   // two) intersections with the support circle; pieces inside the circle use the
   // line primitive, pieces outside contribute the sector term.
@@ -141,6 +169,84 @@ struct SphKernel {
     }
     return result;
   }
+  // The same edge integral arranged for SIMT execution (one edge per lane):
+  // the support circle is convex, so at most one of the three pieces of an edge
+  // lies inside it. The (cheap) sector terms of the outside pieces are summed
+  // first, then every lane makes exactly two calls of the (expensive) line
+  // primitive, predicated on the inside piece existing. Piece boundaries, the
+  // `tiny` skips and the midpoint classification are those of tri_edge above;
+  // only the order of the additions differs.
+  template<int I>
+  __device__ __forceinline__ static double tri_edge_simt(double tiny, bool anti, double eta, double radius_sqr, double sector, double p0x, double p0y, double p1x, double p1y) {
+    const double ex = p1x - p0x, ey = p1y - p0y;
+    const double len2 = ex * ex + ey * ey;
+    const bool edge_ok = len2 > tiny * tiny;
+    const double len = sqrt(edge_ok ? len2 : 1.0);
+    const double tx = ex / len, ty = ey / len;
+    const double delta = p0x * ty - p0y * tx;
+    const double delta_sqr = delta * delta;
+    const double beta_sqr = eta * eta + delta_sqr;
+    const double beta = sqrt(beta_sqr);
+    const double z_start = p0x * tx + p0y * ty;
+    const double z_finish = z_start + len;
+    double m1 = z_start, m2 = z_start;
+    if (radius_sqr > delta_sqr) {
+      const double z_clip = sqrt(radius_sqr - delta_sqr);
+      if (z_start < -z_clip && -z_clip < z_finish) m1 = -z_clip;
+      m2 = m1;
+      if (z_start < +z_clip && +z_clip < z_finish) m2 = +z_clip;
+    }
+    double result = 0.0, in_lo = 0.0, in_hi = 0.0;
+    bool has_in = false;
+    double extra = 0.0;  // a second inside piece cannot exist for a convex support; handled for robustness
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double z_lo = k == 0 ? z_start : k == 1 ? m1 : m2;
+      const double z_hi = k == 0 ? m1 : k == 1 ? m2 : z_finish;
+      if (edge_ok && fabs(z_hi - z_lo) > tiny) {
+        const double zm = 0.5 * (z_lo + z_hi);
+        if (zm * zm + delta_sqr < radius_sqr) {
+          if (!has_in) { has_in = true; in_lo = z_lo; in_hi = z_hi; }
+          else extra += line_prim<I>(tiny, anti, eta, delta, delta_sqr, beta_sqr, beta, z_hi) - line_prim<I>(tiny, anti, eta, delta, delta_sqr, beta_sqr, beta, z_lo);
+        } else {
+          result += sector * atan2(delta * (z_hi - z_lo), fma(z_lo, z_hi, delta_sqr));
+        }
+      }
+    }
+    if (has_in) result += line_prim_delta<I>(tiny, anti, eta, delta, delta_sqr, beta_sqr, beta, in_hi, in_lo);
+    return result + extra;
+  }
+  // Unit integral of one EDGE (0: a->b, 1: b->c, 2: c->a) of a face over all
+  // kernel pieces; the three edges of a face add up to tri_integral().
+  template<int I = 0>
+  __device__ __forceinline__ static double tri_edge_integral(const Params& P, bool anti, double eta, double p0x, double p0y, double p1x, double p1y) {
+    if constexpr (I >= KG::num_pieces) return 0.0;
+    else {
+      const double cut = KG::cutoff(I);
+      double r = 0.0;
+      if (eta < cut) {
+        const double sector = anti ? KG::template tri_antigrad_sector<I>(eta) : KG::template tri_flux_sector<I>(eta);
+        r = tri_edge_simt<I>(P.tiny, anti, eta, cut * cut - eta * eta, sector, p0x, p0y, p1x, p1y);
+      }
+      return r + tri_edge_integral<I + 1>(P, anti, eta, p0x, p0y, p1x, p1y);
+    }
+  }
+  // One edge's share of face_integral<Anti>(P, f, x) (3-D).
+  template<bool Anti>
+  __device__ __forceinline__ static double face_edge_integral(const Params& P, const FaceFrame<3>& f, const Vec<3>& x, int edge) {
+    const double ax = f.a[0] - x[0], ay = f.a[1] - x[1], az = f.a[2] - x[2];
+    const double d = -(ax * f.n[0] + ay * f.n[1] + az * f.n[2]) * P.hinv;
+    const double pax = (ax * f.e1[0] + ay * f.e1[1] + az * f.e1[2]) * P.hinv;
+    const double pay = (ax * f.e2[0] + ay * f.e2[1] + az * f.e2[2]) * P.hinv;
+    const double pbx = pax + f.bx * P.hinv, pby = pay;
+    const double pcx = pax + f.cx * P.hinv, pcy = pay + f.cy * P.hinv;
+    const double p0x = edge == 0 ? pax : edge == 1 ? pbx : pcx, p0y = edge == 0 ? pay : edge == 1 ? pby : pcy;
+    const double p1x = edge == 0 ? pbx : edge == 1 ? pcx : pax, p1y = edge == 0 ? pby : edge == 1 ? pcy : pay;
+    const double u = tri_edge_integral(P, Anti, fabs(d), p0x, p0y, p1x, p1y);
+    if constexpr (Anti) return copysign(P.w_anti, d) * u;
+    else return P.w_flux * u;
+  }
+
   template<int I>
   TIT_HD static double tri_piece(const Params& P, bool anti, double eta, const double* a, const double* b, const double* c) {
     const double cut = KG::cutoff(I);

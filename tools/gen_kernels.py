@@ -351,6 +351,61 @@ def emit_recurrence_line(name, w, cutoff, kind: str) -> str:
     return "\n".join(out)
 
 
+def emit_recurrence_line_delta(name, w, cutoff, kind: str) -> str:
+    """F(z1) - F(z0) of the 3D edge primitive from ONE pass of the J/K recurrences.
+
+    The recurrences are linear in their seeds (z rho^p, L, A), so the difference
+    of two evaluations on the same line (same eta, delta) obeys the same
+    recurrences with the seeds replaced by their differences; dA and dL arrive
+    as single transcendentals (sph_kernel.cuh, line_prim_delta). Product only:
+    halves the arithmetic of the wall pass, same value up to rounding.
+    """
+    if kind == "flux":
+        mom = coeffs(flux_moment(w, rho), rho)
+        kmax = max(mom)
+    else:
+        tm = tail_moment_poly(w, cutoff, 3)
+        kmax = max(max(tm) - 1, 1)
+    jmax = max(kmax - 2, 1)
+    out = [
+        f"TIT_HD static double {name}(double eta, double delta, double z1, double rho1, double z0, double rho0, double dA, double dL) {{",
+        "  const double e2 = eta * eta;",
+        "  const double b2 = fma(delta, delta, e2);",
+        "  const double s1 = fma(z1, z1, b2), s0 = fma(z0, z0, b2);",
+        "  double p1[%d], p0[%d]; p1[0] = 1.0; p0[0] = 1.0; p1[1] = rho1; p0[1] = rho0;" % (jmax + 1, jmax + 1),
+    ]
+    for p in range(2, jmax + 1):
+        out.append(f"  p1[{p}] = p1[{p - 2}] * s1; p0[{p}] = p0[{p - 2}] * s0;")
+    out.append("  double J[%d];" % (jmax + 1))
+    out.append("  J[0] = z1 - z0;")
+    out.append("  J[1] = 0.5 * fma(b2, dL, fma(z1, rho1, -(z0 * rho0)));")
+    for p in range(2, jmax + 1):
+        out.append(f"  J[{p}] = fma({p}.0 * b2, J[{p - 2}], fma(z1, p1[{p}], -(z0 * p0[{p}]))) * (1.0 / {p + 1}.0);")
+    out.append("  double K[%d];" % (kmax + 1))
+    out.append("  K[0] = dA;")
+    out.append("  K[1] = delta * dL;")
+    for p in range(2, kmax + 1):
+        out.append(f"  K[{p}] = fma(delta, J[{p - 2}], e2 * K[{p - 2}]);")
+    acc = []
+    if kind == "flux":
+        for p, c in mom.items():
+            if p == 0:
+                acc.append(f"({horner_eta(coeffs(c, eta))}) * K[0]")
+            else:
+                acc.append(f"{lit(c)} * K[{p}]")
+    else:
+        k0 = {0: tm.get(0, 0)}
+        for p, c in tm.items():
+            if p == 0:
+                continue
+            acc.append(f"{lit(c / (p - 1))} * eta * K[{p - 1}]")
+            k0[p] = k0.get(p, 0) - c / (p - 1)
+        acc.append(f"({horner_eta(k0)}) * K[0]")
+    out.append("  return " + "\n       + ".join(acc) + ";")
+    out.append("}")
+    return "\n".join(out)
+
+
 def emit_sector(name, expr, qual) -> str:
     return f"{qual} double {name}(double eta) {{\n  return {horner_eta(coeffs(expr, eta))};\n}}"
 
@@ -438,6 +493,8 @@ def generate_product(path):
             out.append(emit_recurrence_seg(f"seg_antigrad_{i}", tail_moment_poly(w, c, 2), "antigrad"))
             out.append(emit_recurrence_line(f"tri_flux_line_{i}", w, c, "flux"))
             out.append(emit_recurrence_line(f"tri_antigrad_line_{i}", w, c, "antigrad"))
+            out.append(emit_recurrence_line_delta(f"tri_flux_line_delta_{i}", w, c, "flux"))
+            out.append(emit_recurrence_line_delta(f"tri_antigrad_line_delta_{i}", w, c, "antigrad"))
             out.append(emit_sector(f"tri_flux_sector_{i}", tri_flux_sector_sym(w, c), "TIT_HD static"))
             out.append(emit_sector(f"tri_antigrad_sector_{i}", tri_antigrad_sector_sym(w, c), "TIT_HD static"))
         for fn, params in (
@@ -445,6 +502,8 @@ def generate_product(path):
             ("seg_antigrad", "double eta, double z, double rho, double A, double L"),
             ("tri_flux_line", "double eta, double delta, double z, double rho, double A, double L"),
             ("tri_antigrad_line", "double eta, double delta, double z, double rho, double A, double L"),
+            ("tri_flux_line_delta", "double eta, double delta, double z1, double rho1, double z0, double rho0, double dA, double dL"),
+            ("tri_antigrad_line_delta", "double eta, double delta, double z1, double rho1, double z0, double rho0, double dA, double dL"),
             ("tri_flux_sector", "double eta"),
             ("tri_antigrad_sector", "double eta"),
         ):
