@@ -32,6 +32,7 @@ template<> struct FaceFrame<2> {
 template<> struct FaceFrame<3> {
   double a[3], n[3], e1[3], e2[3];
   double bx, cx, cy;
+  double et[3][2], elen[3];  // unit tangent and length of the edges a->b, b->c, c->a in the (e1, e2) frame
   double ctr[3];
   double lo[3], hi[3];
   unsigned v[3];
@@ -177,12 +178,10 @@ struct SphKernel {
   // `tiny` skips and the midpoint classification are those of tri_edge above;
   // only the order of the additions differs.
   template<int I>
-  __device__ __forceinline__ static double tri_edge_simt(double tiny, bool anti, double eta, double radius_sqr, double sector, double p0x, double p0y, double p1x, double p1y) {
-    const double ex = p1x - p0x, ey = p1y - p0y;
-    const double len2 = ex * ex + ey * ey;
-    const bool edge_ok = len2 > tiny * tiny;
-    const double len = sqrt(edge_ok ? len2 : 1.0);
-    const double tx = ex / len, ty = ey / len;
+  __device__ __forceinline__ static double tri_edge_simt(double tiny, bool anti, double eta, double radius_sqr, double sector, double p0x, double p0y, double tx, double ty, double len) {
+    // (tx, ty) and len come precomputed with the face (the reference re-derives
+    // them from the projected end points on every evaluation).
+    const bool edge_ok = len > tiny;
     const double delta = p0x * ty - p0y * tx;
     const double delta_sqr = delta * delta;
     const double beta_sqr = eta * eta + delta_sqr;
@@ -219,16 +218,16 @@ struct SphKernel {
   // Unit integral of one EDGE (0: a->b, 1: b->c, 2: c->a) of a face over all
   // kernel pieces; the three edges of a face add up to tri_integral().
   template<int I = 0>
-  __device__ __forceinline__ static double tri_edge_integral(const Params& P, bool anti, double eta, double p0x, double p0y, double p1x, double p1y) {
+  __device__ __forceinline__ static double tri_edge_integral(const Params& P, bool anti, double eta, double p0x, double p0y, double tx, double ty, double len) {
     if constexpr (I >= KG::num_pieces) return 0.0;
     else {
       const double cut = KG::cutoff(I);
       double r = 0.0;
       if (eta < cut) {
         const double sector = anti ? KG::template tri_antigrad_sector<I>(eta) : KG::template tri_flux_sector<I>(eta);
-        r = tri_edge_simt<I>(P.tiny, anti, eta, cut * cut - eta * eta, sector, p0x, p0y, p1x, p1y);
+        r = tri_edge_simt<I>(P.tiny, anti, eta, cut * cut - eta * eta, sector, p0x, p0y, tx, ty, len);
       }
-      return r + tri_edge_integral<I + 1>(P, anti, eta, p0x, p0y, p1x, p1y);
+      return r + tri_edge_integral<I + 1>(P, anti, eta, p0x, p0y, tx, ty, len);
     }
   }
   // One edge's share of face_integral<Anti>(P, f, x) (3-D).
@@ -238,11 +237,9 @@ struct SphKernel {
     const double d = -(ax * f.n[0] + ay * f.n[1] + az * f.n[2]) * P.hinv;
     const double pax = (ax * f.e1[0] + ay * f.e1[1] + az * f.e1[2]) * P.hinv;
     const double pay = (ax * f.e2[0] + ay * f.e2[1] + az * f.e2[2]) * P.hinv;
-    const double pbx = pax + f.bx * P.hinv, pby = pay;
-    const double pcx = pax + f.cx * P.hinv, pcy = pay + f.cy * P.hinv;
-    const double p0x = edge == 0 ? pax : edge == 1 ? pbx : pcx, p0y = edge == 0 ? pay : edge == 1 ? pby : pcy;
-    const double p1x = edge == 0 ? pbx : edge == 1 ? pcx : pax, p1y = edge == 0 ? pby : edge == 1 ? pcy : pay;
-    const double u = tri_edge_integral(P, Anti, fabs(d), p0x, p0y, p1x, p1y);
+    const double p0x = pax + (edge == 0 ? 0.0 : edge == 1 ? f.bx : f.cx) * P.hinv;
+    const double p0y = pay + (edge == 2 ? f.cy : 0.0) * P.hinv;
+    const double u = tri_edge_integral(P, Anti, fabs(d), p0x, p0y, f.et[edge][0], f.et[edge][1], f.elen[edge] * P.hinv);
     if constexpr (Anti) return copysign(P.w_anti, d) * u;
     else return P.w_flux * u;
   }
