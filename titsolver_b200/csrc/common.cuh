@@ -169,6 +169,7 @@ struct Params {
   int nf, nx, n;
   int n_owned;    // slab decomposition: fluid particles [n_owned, nf) are ghosts (neighbours only); == nf otherwise
   float pre_thr;  // FP32 pre-filter threshold on the squared distance in cell units
+  float face_thr; // same for the face cull (face-grid cell units)
   float oor;      // |grid coordinate| beyond which the FP32 pre-filter is bypassed
   GridDesc grid;   // particle hash
   GridDesc fgrid;  // face index + per-cell wall / containment flags

@@ -230,18 +230,18 @@ struct SphKernel {
       return r + tri_edge_integral<I + 1>(P, anti, eta, p0x, p0y, tx, ty, len);
     }
   }
-  // One edge's share of face_integral<Anti>(P, f, x) (3-D).
-  template<bool Anti>
-  __device__ __forceinline__ static double face_edge_integral(const Params& P, const FaceFrame<3>& f, const Vec<3>& x, int edge) {
+  // One edge's share of face_integral<Anti>(P, f, x) (3-D). Deliberately ONE
+  // out-of-line copy serving both the flux and the antigradient pass: the wall
+  // kernel is instruction-fetch sensitive.
+  __device__ __noinline__ static double face_edge_integral(const Params& P, const FaceFrame<3>& f, const Vec<3>& x, int edge, bool anti) {
     const double ax = f.a[0] - x[0], ay = f.a[1] - x[1], az = f.a[2] - x[2];
     const double d = -(ax * f.n[0] + ay * f.n[1] + az * f.n[2]) * P.hinv;
     const double pax = (ax * f.e1[0] + ay * f.e1[1] + az * f.e1[2]) * P.hinv;
     const double pay = (ax * f.e2[0] + ay * f.e2[1] + az * f.e2[2]) * P.hinv;
     const double p0x = pax + (edge == 0 ? 0.0 : edge == 1 ? f.bx : f.cx) * P.hinv;
     const double p0y = pay + (edge == 2 ? f.cy : 0.0) * P.hinv;
-    const double u = tri_edge_integral(P, Anti, fabs(d), p0x, p0y, f.et[edge][0], f.et[edge][1], f.elen[edge] * P.hinv);
-    if constexpr (Anti) return copysign(P.w_anti, d) * u;
-    else return P.w_flux * u;
+    const double u = tri_edge_integral(P, anti, fabs(d), p0x, p0y, f.et[edge][0], f.et[edge][1], f.elen[edge] * P.hinv);
+    return (anti ? copysign(P.w_anti, d) : P.w_flux) * u;
   }
 
   template<int I>
