@@ -101,6 +101,21 @@ TITGPU_API int titgpu_step(titgpu_ctx* ctx, int nsteps, double* dt_last);
  * The state evolution is identical at every level. */
 TITGPU_API int titgpu_set_outputs(titgpu_ctx* ctx, int level);
 
+/* Step-persistent candidate lists (default OFF; titgpu_set_lists(ctx, 1) or the
+ * environment TITGPU_LISTS=1 turns them on). The reference searches the neighbours at each of the four
+ * prepare() calls of a step (sph/time_integrator.hpp:161-184). With lists the
+ * cell sweep runs once per step with the radius enlarged by a skin of 0.1
+ * radii, and every neighbour pass of the step applies the exact test to the
+ * current positions of the listed candidates: the neighbour sets used are the
+ * reference's. Should a particle move more than half the skin within a step
+ * (beyond Mach 1/3 under the CFL limit) or a list overflow, the titgpu_step call
+ * is repeated from its saved initial state with a search at every prepare;
+ * titgpu_list_redos counts such calls. SSPRK integrators, single context.
+ * Measured on B200 the lists do not pay (the pair passes are bound by the
+ * gathers of the neighbour records, not by the cell sweep): kept as an option. */
+TITGPU_API int titgpu_set_lists(titgpu_ctx* ctx, int on);
+TITGPU_API unsigned long long titgpu_list_redos(const titgpu_ctx* ctx);
+
 /* ParticleMesh adjacency (particle_mesh.hpp:67-72, 137-147): CSR, rows in
  * original particle order, columns ascending, self included. Call with
  * cols == NULL to obtain nnz. */

@@ -209,6 +209,44 @@ def test_output_levels_do_not_change_the_state(oracle):
         g.set_outputs(3)
 
 
+def _run(case, lists, v=None, nsteps=3, dim=2):
+    g = tb.Solver(dim)
+    tb.load_case(g, case)
+    g.set_lists(lists)
+    if v is not None:
+        g.upload("v", v)
+    g.initialize()
+    g.step(nsteps)
+    return g, [g.download(f) for f in STEP_FIELDS]
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_candidate_lists_match_search_at_every_prepare(dim):
+    """titgpu_set_lists: one skin-enlarged search per step vs the reference's four;
+    the neighbour sets are the same, only the order of the sums differs."""
+    case = cases.dam_break_2d(24) if dim == 2 else case_3d()
+    g1, a = _run(case, True, dim=dim)
+    g0, b = _run(case, False, dim=dim)
+    assert g1.list_redos == 0
+    for x, y in zip(a, b):
+        assert rel_err(x, y) <= 1e-11
+
+
+def test_candidate_lists_fall_back_when_the_skin_is_exceeded():
+    """Near-sonic velocities move particles by more than skin / 2 in one step: the
+    call is repeated with a search at every prepare and gives that result (up to the
+    order of the sums: the hash cells are a skin wider when lists are enabled)."""
+    case = cases.dam_break_2d(16)
+    rng = np.random.default_rng(5)
+    v = np.zeros_like(case.r)
+    v[: case.n_fluid] = rng.normal(size=(case.n_fluid, 2)) * case.cs0
+    g1, a = _run(case, True, v, nsteps=2)
+    g0, b = _run(case, False, v, nsteps=2)
+    assert g1.list_redos == 1 and g0.list_redos == 0
+    for x, y in zip(a, b):
+        assert rel_err(x, y) <= 1e-9
+
+
 def test_strided_upload_download(oracle):
     """The reference pads Vec<double,3> to 32 bytes."""
     case = cases.dam_break_3d(4)

@@ -30,7 +30,7 @@ FIELDS = {
 ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
-    "titgpu_set_outputs", "titgpu_mg_reserve", "titgpu_mg_counts", "titgpu_mg_export", "titgpu_mg_import", "titgpu_mg_set_exchange", "titgpu_mg_scalars",
+    "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_mg_reserve", "titgpu_mg_counts", "titgpu_mg_export", "titgpu_mg_import", "titgpu_mg_set_exchange", "titgpu_mg_scalars",
     "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
     "titgpu_profile_enable", "titgpu_profile_reset", "titgpu_profile_count", "titgpu_profile_get", "titgpu_measure_fp64_peak",
 ]
@@ -69,6 +69,9 @@ def load_library() -> C.CDLL:
     lib.titgpu_step.argtypes = [vp, C.c_int, C.POINTER(d)]
     lib.titgpu_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
     lib.titgpu_set_outputs.argtypes = [vp, C.c_int]
+    lib.titgpu_set_lists.argtypes = [vp, C.c_int]
+    lib.titgpu_list_redos.argtypes = [vp]
+    lib.titgpu_list_redos.restype = C.c_ulonglong
     lib.titgpu_mg_reserve.argtypes = [vp, sz]
     lib.titgpu_mg_counts.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
     lib.titgpu_mg_export.argtypes = [vp, vp, vp, vp, vp]
@@ -183,6 +186,14 @@ class Solver:
     def set_outputs(self, level):
         """0 state only, 1 + derived fields of fluid particles, 2 everything (reference, default)."""
         self._ck(self.lib.titgpu_set_outputs(self.h, int(level)), "titgpu_set_outputs")
+
+    def set_lists(self, on):
+        """Step-persistent candidate lists on / off (titgpu_set_lists)."""
+        self._ck(self.lib.titgpu_set_lists(self.h, int(bool(on))), "titgpu_set_lists")
+
+    @property
+    def list_redos(self):
+        return int(self.lib.titgpu_list_redos(self.h))
 
     # ---- slab decomposition (see slab.py) ----
     def mg_reserve(self, max_fluid):

@@ -170,6 +170,8 @@ struct Params {
   int n_owned;    // slab decomposition: fluid particles [n_owned, nf) are ghosts (neighbours only); == nf otherwise
   float pre_thr;  // FP32 pre-filter threshold on the squared distance in cell units
   float face_thr; // same for the face cull (face-grid cell units)
+  float list_thr; // FP32 threshold of the candidate-list build: ((radius + skin) / cell)^2 + margin
+  double skin_half2;  // (skin / 2)^2: a particle that moves farther than this from where the lists were built invalidates them
   float oor;      // |grid coordinate| beyond which the FP32 pre-filter is bypassed
   GridDesc grid;   // particle hash
   GridDesc fgrid;  // face index + per-cell wall / containment flags

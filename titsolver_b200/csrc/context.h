@@ -63,6 +63,15 @@ struct Ctx {
   size_t reserve_fluid = 0, cap_n = 0;
   int (*exchange_fn)(void*, int) = nullptr;
   void* exchange_user = nullptr;
+  // Step-persistent candidate lists (engine.cuh, "candidate lists"): built once
+  // per step with a skin, reused by every neighbour pass of the step.
+  bool lists_enabled = false;  // titgpu_set_lists / TITGPU_LISTS=1 (measured: no gain on B200)
+  bool lists_active = false;   // valid for the current particle order
+  bool force_safe = false;     // redo in progress: search at every prepare, as the reference does
+  int nl_stride = 0;
+  DBuf nl_idx, nl_cnt;
+  DBuf bakA, bakB, bak_orig;   // state at the beginning of a titgpu_step call (redo)
+  unsigned long long list_redos = 0;  // titgpu_step calls that had to be repeated without lists
   int output_level = 2;  // titgpu_set_outputs: 0 state only, 1 + derived fields of fluid particles, 2 all (reference)
 
   // Packed particle records in sorted order (see engine.cuh): A = position +

@@ -2,6 +2,7 @@
 // and sizes only; dispatches to the (dimension, kernel) engine instantiation.
 #include "../../include/titgpu.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -122,6 +123,7 @@ int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_
   TIT_CUDA_OK(c, cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   TIT_CUDA_OK(c, cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
   c.prm.eos = eos_id;
+  if (const char* e = std::getenv("TITGPU_LISTS")) c.lists_enabled = e[0] != '0';
   return 0;
 }
 
@@ -134,7 +136,7 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (DBuf& b : c.buf_orig) b.release();
   for (DBuf* b : {&c.C, &c.F, &c.gamma_w, &c.gg_w, &c.wsum, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.fs_flag, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm,
                   &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
-                  &c.rho_fx, &c.p_fx, &c.staging, &c.scalars})
+                  &c.rho_fx, &c.p_fx, &c.staging, &c.scalars, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
     b->release();
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
   for (auto& p : c.prof_pending) { cudaEventDestroy(p.beg); cudaEventDestroy(p.end); }
@@ -286,6 +288,15 @@ int titgpu_step(titgpu_ctx* h, int nsteps, double* dt_last) {
   if (dt_last) *dt_last = dt;
   TITGPU_LEAVE()
 }
+int titgpu_set_lists(titgpu_ctx* h, int on) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  c.lists_enabled = on != 0;
+  c.lists_active = false;
+  c.grid_ready = false;  // the cell size depends on the skin
+  return 0;
+}
+unsigned long long titgpu_list_redos(const titgpu_ctx* h) { return h ? h->c.list_redos : 0; }
 int titgpu_set_outputs(titgpu_ctx* h, int level) {
   if (!h) return 1;
   Ctx& c = h->c;
