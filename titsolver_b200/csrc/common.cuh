@@ -98,26 +98,44 @@ template<int D> TIT_HD Mat<D> matmul(const Mat<D>& A, const Mat<D>& B) {
 // LU without pivoting; fails on a tiny pivot (core/_mat/fact.hpp:84-108), then
 // inverse via unit-lower / upper solves of the identity (part.hpp:100-125).
 template<int D> TIT_HD bool lu_inverse(const Mat<D>& A, Mat<D>& inv, double tiny) {
+  // Every loop has compile-time bounds after unrolling: the factors stay in
+  // registers (dynamically indexed copies would live in local memory).
   Mat<D> LU = mzero<D>();
+#pragma unroll
   for (int i = 0; i < D; ++i) {
-    for (int j = 0; j < i; ++j) {
-      double s = A[i][j];
-      for (int k = 0; k < j; ++k) s -= LU[i][k] * LU[k][j];
-      LU[i][j] = s / LU[j][j];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (j < i) {
+        double s = A[i][j];
+#pragma unroll
+        for (int k = 0; k < D; ++k) if (k < j) s -= LU[i][k] * LU[k][j];
+        LU[i][j] = s / LU[j][j];
+      }
     }
-    for (int j = i; j < D; ++j) {
-      double s = A[i][j];
-      for (int k = 0; k < i; ++k) s -= LU[i][k] * LU[k][j];
-      LU[i][j] = s;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (j >= i) {
+        double s = A[i][j];
+#pragma unroll
+        for (int k = 0; k < D; ++k) if (k < i) s -= LU[i][k] * LU[k][j];
+        LU[i][j] = s;
+      }
     }
     if (fabs(LU[i][i]) <= tiny) return false;
   }
   Mat<D> x = meye<D>();
-  for (int i = 0; i < D; ++i)
-    for (int j = 0; j < i; ++j) x[i] -= LU[i][j] * x[j];
-  for (int i = D - 1; i >= 0; --i) {
-    for (int j = i + 1; j < D; ++j) x[i] -= LU[i][j] * x[j];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) if (j < i) x[i] -= LU[i][j] * x[j];
+  }
+#pragma unroll
+  for (int ii = 0; ii < D; ++ii) {
+    const int i = D - 1 - ii;
+#pragma unroll
+    for (int j = 0; j < D; ++j) if (j > i) x[i] -= LU[i][j] * x[j];
     const double dinv = LU[i][i];
+#pragma unroll
     for (int c = 0; c < D; ++c) x[i][c] = x[i][c] / dinv;
   }
   inv = x;

@@ -94,7 +94,7 @@ struct Ctx {
   DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp;
 
   // Static boundary.
-  DBuf frames, fcell_start, fcell_faces, face_cells, fflag;
+  DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin;
   size_t nfaces = 0;
   DBuf cverts, cfaces;
   size_t ncfaces = 0;
@@ -107,7 +107,8 @@ struct Ctx {
   DBuf staging;
 
   // Device scalars: [0] dt, [1] max |dv_dt|^2 of the last RHS (bits), [2] dt
-  // reduction (bits), [3] spare.
+  // reduction (bits), [3] spare, [4] candidate-list flags, [5] backup of [1],
+  // [6] (int) set by an upload of `r` that moves a wall particle.
   DBuf scalars;
 
   // Host copies of the surfaces.

@@ -135,7 +135,7 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (DBuf& b : c.bufB) b.release();
   for (DBuf& b : c.buf_orig) b.release();
   for (DBuf* b : {&c.C, &c.F, &c.gamma_w, &c.gg_w, &c.wsum, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.fs_flag, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm,
-                  &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
+                  &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.ftwin, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
                   &c.rho_fx, &c.p_fx, &c.staging, &c.scalars, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
     b->release();
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
@@ -211,10 +211,16 @@ int titgpu_upload(titgpu_ctx* h, size_t n_fluid, size_t n_fixed, const char* fie
     return 0;
   }
   TIT_CUDA_OK(c, cudaMemcpyAsync(c.staging.p, src, bytes, cudaMemcpyHostToDevice, c.stream));
+  // Wall particles never move in the reference's time loop (wcsph.cpp:170-193): their
+  // gamma / grad gamma cache survives an upload of `r` that leaves them where they were.
+  const bool track_walls = f == F_r && c.fixed_cache_valid && c.grid_ready;
+  if (track_walls) TIT_CUDA_OK(c, cudaMemsetAsync(c.scalars.as<int>() + 12, 0, 4, c.stream));
   if (c.vt->upload_state(c, f, c.staging.as<double>())) return 1;
+  int moved = 1;
+  if (track_walls) TIT_CUDA_OK(c, cudaMemcpyAsync(&moved, c.scalars.as<int>() + 12, 4, cudaMemcpyDeviceToHost, c.stream));
   TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
   c.prof_fold();
-  if (f == F_r) { c.fixed_cache_valid = false; }
+  if (f == F_r && moved) { c.fixed_cache_valid = false; }
   return 0;
 }
 

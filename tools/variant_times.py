@@ -17,6 +17,7 @@ warm = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 case = cases.dam_break_2d(n_col) if dim == 2 else cases.dam_break_3d(n_col)
 s = tb.Solver(dim)
 tb.load_case(s, case)
+s.set_lists(int(os.environ.get('TIT_LISTS', '0')))
 s.initialize()
 s.set_outputs(0)
 s.step(warm)
@@ -36,5 +37,5 @@ for f in ("r", "v", "rho"):
 tot = sum(v[1] for v in prof.values())
 out = {"lib": os.path.basename(tb.LIB_PATH), "n": case.n, "ms_per_step": round(tot / steps, 3),
        "kernels_ms_per_step": {k: round(v[1] / steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:9]},
-       "sha1": h.hexdigest()[:12], "abs_sums": sums}
+       "lists": int(os.environ.get("TIT_LISTS", "0")), "redos": s.list_redos, "sha1": h.hexdigest()[:12], "abs_sums": sums}
 print(json.dumps(out), flush=True)
