@@ -230,10 +230,9 @@ struct SphKernel {
       return r + tri_edge_integral<I + 1>(P, anti, eta, p0x, p0y, tx, ty, len);
     }
   }
-  // One edge's share of face_integral<Anti>(P, f, x) (3-D). Deliberately ONE
-  // out-of-line copy serving both the flux and the antigradient pass: the wall
-  // kernel is instruction-fetch sensitive.
-  __device__ __noinline__ static double face_edge_integral(const Params& P, const FaceFrame<3>& f, const Vec<3>& x, int edge, bool anti) {
+  // One edge's share of face_integral<Anti>(P, f, x) (3-D); `anti` selects the
+  // primitive at run time so that k_weval holds one copy of the code for both passes.
+  __device__ __forceinline__ static double face_edge_integral(const Params& P, const FaceFrame<3>& f, const Vec<3>& x, int edge, bool anti) {
     const double ax = f.a[0] - x[0], ay = f.a[1] - x[1], az = f.a[2] - x[2];
     const double d = -(ax * f.n[0] + ay * f.n[1] + az * f.n[2]) * P.hinv;
     const double pax = (ax * f.e1[0] + ay * f.e1[1] + az * f.e1[2]) * P.hinv;
