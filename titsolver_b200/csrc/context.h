@@ -91,10 +91,10 @@ struct Ctx {
   DBuf gamma_s, N_s, phi_s, phi2_s, dr_s, gv_s, gr_s, fs_flag;  // post-integration scratch
 
   // Hash / sort scratch.
-  DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp, cell_fs;
+  DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp, cell_fs, cell_fluid;
 
   // Static boundary.
-  DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin;
+  DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin, fterm;
   // 3-D wall pipeline work lists (engine.cuh, k_wsearch) and their capacities in entries.
   DBuf ww_faces, ww_sref, ww_items, ww_val, ww_rims, ww_val2, ww_act, ww_ovf, ww_x2, ww_cur;
   size_t ww_cap_faces = 0, ww_cap_items = 0, ww_cap_rims = 0, ww_cap_act = 0;
