@@ -17,9 +17,15 @@ if has l; then
   echo "launch list rc=$?"
 fi
 if has f; then
-  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k 'regex:k_rhs|k_wall|k_shift_sums' -c 8 \
+  # One substep's kernels (boundary extrapolation, the five wall stages, k_rhs), then k_shift_sums.
+  # Reports must stay small: gpurun brings back at most 64 MiB.
+  timeout 900 ncu --set full --clock-control none --profile-from-start off -k 'regex:k_rhs|k_w|k_setup' -c ${NCU_COUNT:-7} \
     -o gpurun_out/${tag}_full -f python tools/prof_step.py 3 ${NCOL_FULL:-110} 1 > gpurun_out/${tag}_full.log 2>&1
   echo "full capture rc=$?"
+  timeout 900 ncu --set full --clock-control none --profile-from-start off -k 'regex:k_shift_sums' -c 1 \
+    -o gpurun_out/${tag}_full_shift -f python tools/prof_step.py 3 ${NCOL_FULL:-110} 1 > gpurun_out/${tag}_full_shift.log 2>&1
+  echo "full capture (shift) rc=$?"
+  du -sh gpurun_out
 fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.csv 2>&1
 ls -la gpurun_out | tail -20
