@@ -81,6 +81,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(dim, n):
+    """DRAM bytes (read + write) of one k_rhs launch over n particles, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json: bytes per particle measured at the
+    capture's size, scaled to this launch); None when no capture exists for this dimension."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get("k_rhs", {}).get(f"{dim}d")
+    except (OSError, ValueError):
+        return None, None
+    if not rec:
+        return None, None
+    return rec["bytes_per_particle"] * n, rec["source"]
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -128,6 +143,13 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_sample(dim, budget_s=15.0, n_col=None):
     """Time the CPU restatement (oracle, -O3 OpenMP build) on a bounded sample of
     the same workload; returns the cpu_baseline object."""
@@ -137,6 +159,7 @@ def cpu_baseline_sample(dim, budget_s=15.0, n_col=None):
         n_col = 200 if dim == 2 else 28
     case = make_case(dim, n_col)
     s = oracle_lib.OracleSolver(dim, fast=True)
+    s.lib.orc_set_num_threads(host_threads())
     oracle_lib.load_case(s, case)
     s.initialize()
     s.step(1)  # warm-up (first-touch, thread pool)
@@ -166,6 +189,7 @@ def run_reference(args, rank, world):
     n_col = args.ref_n_col or (200 if dim == 2 else 28)
     case = make_case(dim, n_col)
     s = oracle_lib.OracleSolver(dim, fast=True)
+    s.lib.orc_set_num_threads(host_threads())  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     oracle_lib.load_case(s, case)
     s.initialize()
     for _ in range(args.warmup):
@@ -184,7 +208,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference (OpenMP); the reference itself (C++26, oneTBB) cannot be built in this image",
     }
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
 
 
 def run_ours(args, rank, local_rank, world):
@@ -341,7 +365,8 @@ def run_ours(args, rank, local_rank, world):
         ach = alg_bytes_rhs(dim) * n / avg_s / 1e9
         flops = alg_flops_rhs(dim) * (case.n_fluid if slab is None else case.meta["n_fluid_global"] / world) / avg_s / 1e12
         roof = {
-            "bound": "hbm", "kernel": rhs_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "bound": "hbm", "kernel": rhs_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic(dim, n)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
+            "traffic_source": ncu_traffic(dim, n)[1],
             "peak_source": peak_src, "alg_bytes_per_particle": alg_bytes_rhs(dim), "launches": cnt, "avg_ms": avg_s * 1e3,
             "share_of_step": tot / total_kernel_ms if total_kernel_ms else None,
             "fp64": {"achieved_tflops": flops, "peak_tflops": fp64_peak, "frac": flops / fp64_peak if fp64_peak else None,
@@ -353,7 +378,7 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
         cpu, _, _, _ = cpu_baseline_sample(dim, args.cpu_budget)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -369,9 +394,42 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in top[:12]},
     }
-    print(json.dumps(out), flush=True)
+    emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+class QuietStdout:
+    """Everything written to fd 1 while the benchmark runs (NCCL's version banner,
+    library chatter) goes to stderr: stdout carries exactly the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
+def emit(line):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
@@ -390,10 +448,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_ours(args, rank, local_rank, world)
+    global OUT
+    with QuietStdout() as q:
+        OUT = q
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_ours(args, rank, local_rank, world)
+    OUT = None
 
 
 if __name__ == "__main__":
