@@ -181,6 +181,52 @@ def test_one_step_parity_3d(oracle):
     check_step(oracle, case_3d())
 
 
+def test_rhs_parity_3d_shared_edges_second_mesh(oracle):
+    """Every interior edge of the structured wall mesh has a coplanar twin, so the 3-D
+    wall pipeline evaluates it once (flux) or not at all (antigradient rim sum); a second
+    mesh / lattice ratio besides case_3d(). (Ratio 1 is not a parity case: wall particles
+    then see faces that touch their support sphere exactly, see cases.dam_break_3d; the same
+    holds whenever the support radius is a multiple of the wall spacing, e.g. ratio 0.81 here.)"""
+    check_rhs(oracle, cases.dam_break_3d(6, wall_ratio=0.77, jitter=0.13))
+
+
+def test_rhs_parity_3d_fine_wall_mesh_overflows_the_search_stage(oracle):
+    """A wall mesh 2.3x finer than the particle spacing puts > 224 faces within reach of
+    a near-wall particle: the search stage hands those particles to the generic kernel."""
+    case = cases.dam_break_3d(5, wall_ratio=0.43, jitter=0.1)
+    g, c = make_pair(oracle, case)
+    g.initialize()
+    c.initialize()
+    g.profile(True)
+    g.profile_reset()
+    g.rhs_only()
+    c.rhs_only()
+    names = " ".join(g.profile_read())
+    assert "k_wsearch" in names and "k_wall" in names, names
+    nf = case.n_fluid
+    for f in ("gamma", "grad_gamma", "rho"):
+        assert rel_err(g.download(f), c.download(f)) <= TOL, f
+    for f in ("drho_dt", "dv_dt"):
+        assert rel_err(g.download(f)[:nf], c.download(f)[:nf]) <= TOL, f
+
+
+@pytest.mark.parametrize("kernel_id", [0, 2])
+def test_rhs_parity_3d_other_kernels(oracle, kernel_id):
+    check_rhs(oracle, case_3d(5), kernel_id=kernel_id)
+
+
+def test_rhs_parity_3d_linear_eos(oracle):
+    check_rhs(oracle, case_3d(5), eos_id=1)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_one_step_parity_general_tait_exponent(oracle, dim):
+    """xi != 7: the pair loop gathers the neighbours' EOS record instead of recomputing it."""
+    case = cases.dam_break_2d(16) if dim == 2 else case_3d(5)
+    case.xi = 5.0
+    check_step(oracle, case)
+
+
 def test_output_levels_do_not_change_the_state(oracle):
     """titgpu_set_outputs: publishing derived fields is optional, the state evolution is not."""
     case = cases.dam_break_2d(16)
