@@ -293,6 +293,44 @@ def test_candidate_lists_fall_back_when_the_skin_is_exceeded():
         assert rel_err(x, y) <= 1e-9
 
 
+def test_upload_of_r_keeps_or_refreshes_the_wall_cache(oracle):
+    """gamma / grad gamma of the wall particles are cached. An upload of `r` that leaves
+    them in place (every upload of the reference's time loop) keeps the cache; moving one
+    of them rebuilds it - and the results follow the oracle, which has no cache."""
+    case = cases.dam_break_2d(16)
+    g, c = make_pair(oracle, case)
+    g.initialize(); c.initialize()
+    g.step(1)
+    state = {f: g.download(f) for f in ("r", "v", "rho")}
+    for f, a in state.items():
+        c.upload(f, a)
+
+    def launches_of_rhs():
+        n0 = g.launch_count
+        g.rhs_only()
+        return g.launch_count - n0
+
+    def compare():
+        c.rhs_only()
+        nf = case.n_fluid
+        for f in ("gamma", "grad_gamma", "rho"):
+            assert rel_err(g.download(f), c.download(f)) <= TOL, f
+        for f in ("drho_dt", "dv_dt"):
+            assert rel_err(g.download(f)[:nf], c.download(f)[:nf]) <= TOL, f
+
+    launches_of_rhs()
+    base = launches_of_rhs()
+    g.upload("r", state["r"])
+    assert launches_of_rhs() == base  # cache kept
+    compare()
+    moved = state["r"].copy()
+    moved[case.n_fluid + 7] += 0.3 * case.dr * np.array([1.0, 1.0])
+    g.upload("r", moved)
+    c.upload("r", moved)
+    assert launches_of_rhs() == base + 1  # cache rebuilt (2-D: one more wall-kernel launch)
+    compare()
+
+
 def test_strided_upload_download(oracle):
     """The reference pads Vec<double,3> to 32 bytes."""
     case = cases.dam_break_3d(4)
