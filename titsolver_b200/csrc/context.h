@@ -96,7 +96,7 @@ struct Ctx {
   // Static boundary.
   DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin, fterm;
   // 3-D wall pipeline work lists (engine.cuh, k_wsearch) and their capacities in entries.
-  DBuf ww_faces, ww_sref, ww_items, ww_val, ww_rims, ww_val2, ww_act, ww_ovf, ww_x2, ww_cur;
+  DBuf ww_faces, ww_sref, ww_items, ww_val, ww_rims, ww_val2, ww_act, ww_ovf, ww_x2, ww_cur, ww_list;
   size_t ww_cap_faces = 0, ww_cap_items = 0, ww_cap_rims = 0, ww_cap_act = 0;
   size_t nfaces = 0;
   DBuf cverts, cfaces;
