@@ -94,7 +94,7 @@ struct Ctx {
   DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp, cell_fs, cell_fluid;
 
   // Static boundary.
-  DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin, fterm;
+  DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin, fterm, favg;
   // 3-D wall pipeline work lists (engine.cuh, k_wsearch) and their capacities in entries.
   DBuf ww_faces, ww_sref, ww_items, ww_val, ww_rims, ww_val2, ww_act, ww_ovf, ww_x2, ww_cur, ww_list;
   size_t ww_cap_faces = 0, ww_cap_items = 0, ww_cap_rims = 0, ww_cap_act = 0;

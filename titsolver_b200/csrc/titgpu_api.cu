@@ -135,7 +135,7 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (DBuf& b : c.bufB) b.release();
   for (DBuf& b : c.buf_orig) b.release();
   for (DBuf* b : {&c.C, &c.F, &c.gamma_w, &c.gg_w, &c.wsum, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.fs_flag, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm,
-                  &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.cell_fs, &c.cell_fluid, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.ftwin, &c.fterm, &c.ww_faces, &c.ww_sref, &c.ww_items, &c.ww_val, &c.ww_rims, &c.ww_val2, &c.ww_act, &c.ww_ovf, &c.ww_x2, &c.ww_cur, &c.ww_list, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
+                  &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.cell_fs, &c.cell_fluid, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.ftwin, &c.fterm, &c.favg, &c.ww_faces, &c.ww_sref, &c.ww_items, &c.ww_val, &c.ww_rims, &c.ww_val2, &c.ww_act, &c.ww_ovf, &c.ww_x2, &c.ww_cur, &c.ww_list, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
                   &c.rho_fx, &c.p_fx, &c.staging, &c.scalars, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
     b->release();
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
