@@ -19,7 +19,7 @@ fi
 if has f; then
   # One substep's kernels (boundary extrapolation, the five wall stages, k_rhs), then k_shift_sums.
   # Reports must stay small: gpurun brings back at most 64 MiB.
-  timeout 900 ncu --set full --clock-control none --profile-from-start off -k 'regex:k_rhs|k_w|k_setup' -c ${NCU_COUNT:-7} \
+  timeout 900 ncu --set full --clock-control none --profile-from-start off -k 'regex:k_rhs|k_ws|k_we|k_wc|k_wf|k_setup' -c ${NCU_COUNT:-7} \
     -o gpurun_out/${tag}_full -f python tools/prof_step.py 3 ${NCOL_FULL:-110} 1 > gpurun_out/${tag}_full.log 2>&1
   echo "full capture rc=$?"
   timeout 900 ncu --set full --clock-control none --profile-from-start off -k 'regex:k_shift_sums' -c 1 \
