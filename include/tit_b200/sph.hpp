@@ -6,7 +6,7 @@
 // the B200 library (see examples/wcsph.cpp and INTEGRATION.md):
 //
 //   tit::Vec, tit::Mat                              tit/core/vec.hpp, mat.hpp (the subset the driver uses)
-//   tit::geom::Surface, tessellate (2-D)            tit/geom/surface.hpp, tessellation.hpp:30-63
+//   tit::geom::Surface, tessellate (2-D, 3-D)       tit/geom/surface.hpp, tessellation.hpp:30-63, 74-163
 //   tit::geom::MakeFastWinding                      tit/geom/winding/fast_winding.hpp (exact winding, exact_winding.hpp:32-43)
 //   tit::geom::GridSearch, GridFaceSearch, ...      tit/geom/search.hpp, face_search.hpp, partition.hpp (option holders)
 //   tit::sph::Space, ParticleType, field tags       tit/sph/field.hpp:112-218
@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <ranges>
 #include <span>
@@ -147,6 +148,65 @@ auto tessellate(const Surface<V>& surf, vec_num_t<V> d_max) -> Surface<V> {
     }
     result.append_face({prev, last});
   }
+  return result;
+}
+
+/// tit/geom/tessellation.hpp:74-163: red refinement of a triangle surface until no
+/// edge is longer than d_max. Every sweep gives each too-long edge one midpoint
+/// (appended in the order the edges are met: faces in order, edges ab, bc, ca) and
+/// cuts every triangle along its midpoints; vertex and face numbering are those of
+/// the reference (geom/tessellation.test.cpp:64-215). Host-side set-up code.
+template<class V>
+  requires (vec_dim_v<V> == 3)
+auto tessellate(const Surface<V>& surf, vec_num_t<V> d_max) -> Surface<V> {
+  using Num = vec_num_t<V>;
+  using Tri = std::array<std::size_t, 3>;
+  constexpr auto none = static_cast<std::size_t>(-1);
+  std::vector<V> verts(surf.verts().begin(), surf.verts().end());
+  std::vector<Tri> faces(surf.face_verts().begin(), surf.face_verts().end()), next;
+  std::map<std::pair<std::size_t, std::size_t>, std::size_t> mid;
+  const auto key = [](std::size_t i, std::size_t j) { return i < j ? std::pair{i, j} : std::pair{j, i}; };
+  for (;;) {
+    mid.clear();
+    for (const Tri& t : faces) {
+      for (int k = 0; k < 3; ++k) {
+        const std::size_t i = t[k], j = t[(k + 1) % 3];
+        if (mid.contains(key(i, j))) continue;
+        const V e = verts[j] - verts[i];
+        if (dot(e, e) <= d_max * d_max) continue;
+        verts.push_back((verts[i] + verts[j]) / Num{2});
+        mid.emplace(key(i, j), verts.size() - 1);
+      }
+    }
+    if (mid.empty()) break;
+    next.clear();
+    for (const Tri& t : faces) {
+      std::size_t m[3];
+      int n_split = 0;
+      for (int k = 0; k < 3; ++k) {
+        const auto it = mid.find(key(t[k], t[(k + 1) % 3]));
+        m[k] = it == mid.end() ? none : it->second;
+        n_split += m[k] != none;
+      }
+      if (n_split == 0) { next.push_back(t); continue; }
+      // Rotate so that (p, q) is the first split edge in cyclic order.
+      int r = 0;
+      if (n_split < 3) while (!(m[r] != none && m[(r + 2) % 3] == none)) ++r;
+      const std::size_t p = t[r], q = t[(r + 1) % 3], s = t[(r + 2) % 3];
+      const std::size_t m_pq = m[r], m_qs = m[(r + 1) % 3], m_sp = m[(r + 2) % 3];
+      if (n_split == 3) {
+        next.push_back({p, m_pq, m_sp}); next.push_back({m_pq, q, m_qs}); next.push_back({m_sp, m_qs, s}); next.push_back({m_pq, m_qs, m_sp});
+      } else if (n_split == 2) {
+        next.push_back({p, m_pq, s}); next.push_back({m_pq, m_qs, s}); next.push_back({m_pq, q, m_qs});
+      } else {
+        next.push_back({p, m_pq, s}); next.push_back({m_pq, q, s});
+      }
+    }
+    faces.swap(next);
+  }
+  Surface<V> result;
+  for (const V& v : verts) result.append_vert(v);
+  for (const Tri& f : faces) result.append_face(f);
   return result;
 }
 

@@ -235,9 +235,13 @@ def test_face_search_2d(radius, scale):
 @pytest.mark.parametrize("radius", [0.01, 0.1, 0.5, 1.0])
 @pytest.mark.parametrize("scale", [0.5, 5.0])
 def test_face_search_3d(radius, scale):
-    """The reference tessellates a tetrahedron (3-D red refinement, out of scope,
-    SURVEY.md §8f-2); a structured box wall mesh exercises the same index."""
+    """A structured box wall mesh and the reference's own set-up, a red-refined
+    tetrahedron (face_search.test.cpp:136-160, cases.tessellate_3d), exercise the index."""
     pts = reference_cloud(3)
     verts, faces = cases._box_wall_mesh((1.0, 1.0, 1.0), (6, 5, 4))
+    off, cols = oracle_search(pts, radius, scale * radius, 3, verts, faces, want_faces=True)
+    assert csr_rows(off, cols) == brute_faces(verts, faces, pts, radius)
+    tet = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    verts, faces = cases.tessellate_3d(tet, np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]], np.uint64), 0.1)
     off, cols = oracle_search(pts, radius, scale * radius, 3, verts, faces, want_faces=True)
     assert csr_rows(off, cols) == brute_faces(verts, faces, pts, radius)

@@ -2,7 +2,7 @@
 
 Mirrors the reference driver /root/reference/source/titwcsph/wcsph.cpp:37-142
 (constants, tank surface + 2-D tessellation, lattice fill, hydrostatic density)
-and /root/reference/source/tit/geom/tessellation.hpp:30-63 (2-D tessellate).
+and /root/reference/source/tit/geom/tessellation.hpp:30-63 (2-D tessellate), :74-163 (3-D).
 The 3-D case has no reference counterpart: it uses the
 same constants with a structured wall mesh of vertex spacing `wall_dr`.
 """
@@ -71,6 +71,58 @@ def tessellate_2d(verts: np.ndarray, faces: np.ndarray, d_max: float):
             prev = vi
         out_f.append((prev, int(b_i)))
     return np.asarray(out_v, dtype=np.float64), np.asarray(out_f, dtype=np.uint64)
+
+
+def tessellate_3d(verts: np.ndarray, faces: np.ndarray, d_max: float):
+    """geom/tessellation.hpp:74-163: red refinement of a triangle surface until no
+    edge is longer than `d_max`. Per sweep every too-long edge gets ONE midpoint
+    (vertices are appended in the order the edges are met: faces in order, edges
+    ab, bc, ca), then every triangle is cut along its midpoints. With the
+    triangle rotated so that its first split edge is (p, q), the children are
+        3 midpoints   (p, m_pq, m_sp) (m_pq, q, m_qs) (m_sp, m_qs, s) (m_pq, m_qs, m_sp)
+        m_pq + m_qs   (p, m_pq, s) (m_pq, m_qs, s) (m_pq, q, m_qs)
+        m_pq          (p, m_pq, s) (m_pq, q, s)
+    which reproduces the vertex and face numbering of the reference's tests
+    (geom/tessellation.test.cpp:64-215)."""
+    V = [tuple(float(x) for x in v) for v in verts]
+    F = [tuple(int(i) for i in f) for f in faces]
+    d2_max = float(d_max) * float(d_max)
+    while True:
+        mid = {}
+
+        def visit(i, j):
+            key = (i, j) if i < j else (j, i)
+            if key in mid:
+                return
+            a, b = V[i], V[j]
+            if (b[0] - a[0]) ** 2 + (b[1] - a[1]) ** 2 + (b[2] - a[2]) ** 2 <= d2_max:
+                return
+            V.append(((a[0] + b[0]) / 2, (a[1] + b[1]) / 2, (a[2] + b[2]) / 2))
+            mid[key] = len(V) - 1
+
+        for a, b, c in F:
+            visit(a, b); visit(b, c); visit(c, a)
+        if not mid:
+            break
+        out = []
+        for tri in F:
+            m = [mid.get((min(tri[k], tri[(k + 1) % 3]), max(tri[k], tri[(k + 1) % 3]))) for k in range(3)]
+            n_split = sum(x is not None for x in m)
+            if n_split == 0:
+                out.append(tri)
+                continue
+            # rotation: the first split edge in cyclic order whose predecessor is not split (any for 3)
+            r = 0 if n_split == 3 else next(k for k in range(3) if m[k] is not None and m[(k + 2) % 3] is None)
+            p, q, s = tri[r], tri[(r + 1) % 3], tri[(r + 2) % 3]
+            m_pq, m_qs, m_sp = m[r], m[(r + 1) % 3], m[(r + 2) % 3]
+            if n_split == 3:
+                out += [(p, m_pq, m_sp), (m_pq, q, m_qs), (m_sp, m_qs, s), (m_pq, m_qs, m_sp)]
+            elif n_split == 2:
+                out += [(p, m_pq, s), (m_pq, m_qs, s), (m_pq, q, m_qs)]
+            else:
+                out += [(p, m_pq, s), (m_pq, q, s)]
+        F = out
+    return np.asarray(V, dtype=np.float64), np.asarray(F, dtype=np.uint64)
 
 
 def dam_break_2d(n_col: int = 80, H: float = 0.6) -> Case:
