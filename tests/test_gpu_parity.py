@@ -210,6 +210,15 @@ def test_rhs_parity_3d_fine_wall_mesh_overflows_the_search_stage(oracle):
         assert rel_err(g.download(f)[:nf], c.download(f)[:nf]) <= TOL, f
 
 
+def test_rhs_and_step_parity_3d_slanted_refined_walls(oracle):
+    """A tetrahedral tank tessellated by red refinement: slanted faces, irregular
+    triangles, coplanar twins whose normals agree only to rounding."""
+    case = cases.tetra_tank_3d(14, fill=0.7)
+    assert case.n_fluid > 50 and len(case.faces) > 500
+    check_rhs(oracle, case)
+    check_step(oracle, case)
+
+
 @pytest.mark.parametrize("kernel_id", [0, 2])
 def test_rhs_parity_3d_other_kernels(oracle, kernel_id):
     check_rhs(oracle, case_3d(5), kernel_id=kernel_id)

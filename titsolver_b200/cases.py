@@ -265,6 +265,37 @@ def dam_break_3d(n_col: int = 16, H: float = 0.6, wall_ratio: float = 1.0, tank=
                 {"name": f"dam_break_3d_{WM}x{WN}x{WK}", "tank": ext, "wall_ratio": wall_ratio, "jitter": jitter})
 
 
+def tetra_tank_3d(n_side: int = 10, L: float = 1.0, wall_ratio: float = 0.93, jitter: float = 0.1, seed: int = 7, fill: float = 0.55) -> Case:
+    """Fluid in a tetrahedral tank (0,0,0), (L,0,0), (0,L,0), (0,0,L): a wall surface
+    with slanted, red-refined triangles (`tessellate_3d`, the reference's 3-D set-up
+    path, geom/tessellation.hpp:74-163) instead of the axis-aligned structured walls
+    of `dam_break_3d`. The fluid fills the part of the tank below the plane
+    x + y + z = fill * L on a jittered lattice of spacing dr = L / n_side, at least
+    half a spacing away from the walls. Parity cases only (generic positions)."""
+    dr = L / float(n_side)
+    g, rho0 = 9.81, 1000.0
+    cs0 = 20 * math.sqrt(g * L)
+    h0 = 2.0 * dr
+    tet = np.array([[0.0, 0.0, 0.0], [L, 0.0, 0.0], [0.0, L, 0.0], [0.0, 0.0, L]])
+    out_faces = np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]], np.uint64)  # outward normals
+    verts, faces = tessellate_3d(tet, out_faces[:, [0, 2, 1]], wall_ratio * dr)    # normals into the fluid
+    # Containment: the tetrahedron blown up about its centroid so that the wall particles are inside.
+    ctr = tet.mean(axis=0)
+    cverts, cfaces = ctr + (tet - ctr) * (1.0 + 3.0 * dr / L), out_faces
+    k = np.arange(n_side)
+    ii, jj, kk = np.meshgrid(k, k, k, indexing="ij")
+    rf = dr * (np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1) + 0.75)
+    rng = np.random.default_rng(seed)
+    rf = rf + rng.uniform(-jitter, jitter, size=rf.shape) * dr
+    s = rf.sum(axis=1)
+    rf = rf[(rf.min(axis=1) >= 0.5 * dr) & (s <= fill * L)]
+    nf, nx = rf.shape[0], verts.shape[0]
+    r = np.concatenate([rf, verts], axis=0)
+    return Case(dim=3, n_fluid=nf, n_fixed=nx, r=r, m=np.full(nf + nx, rho0 * dr**3), rho=np.full(nf + nx, rho0), verts=verts, faces=faces,
+                cverts=cverts, cfaces=cfaces, g=g, mu=0.001, cs0=cs0, rho0=rho0, xi=7.0, h=h0, dr=dr, H=L,
+                meta={"name": f"tetra_tank_3d_{n_side}", "wall_ratio": wall_ratio, "jitter": jitter})
+
+
 def dam_break_3d_slab(n_col: int, world: int, rank: int, H: float = 0.6, tank=(5.366, 4.0, 1.0), halo_cells: int = 26):
     """Rank-local part of the weak-scaling 3-D dam break: the tank of
     `dam_break_3d` made `world` times deeper along z (the flow is z-invariant, so
