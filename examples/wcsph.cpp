@@ -6,16 +6,19 @@
 // statements and order (wcsph.cpp:36-193). Differences, all at the edges:
 //   * the resolution, the number of steps and an output file come from argv
 //     (the reference hard-codes dr = H/80 and runs to t sqrt(g/H) = 10);
-//   * instead of particles.write(time, series) into a .ttdb storage (out of
-//     scope) the final r, v, rho are dumped as raw doubles;
+//   * the path of the .ttdb storage comes from argv too ("-" = no storage;
+//     the reference always writes ./particles.ttdb), and the final r, v, rho
+//     can also be dumped as raw doubles;
 //   * between output frames only the state is published (particles.publish).
 //
-//   wcsph [n_col=80] [max_steps=0 (run to the end)] [dump.bin]
+//   wcsph [n_col=80] [max_steps=0 (run to the end)] [dump.bin|-] [particles.ttdb|-]
 #include <chrono>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <numbers>
+#include <optional>
+#include <string_view>
 
 #include "tit_b200/sph.hpp"
 
@@ -26,7 +29,8 @@ template<class Real>
 auto sph_main(int argc, char** argv) -> int {
   const int n_col = argc > 1 ? std::atoi(argv[1]) : 80;
   const std::size_t max_steps = argc > 2 ? std::strtoull(argv[2], nullptr, 10) : 0;
-  const char* dump = argc > 3 ? argv[3] : nullptr;
+  const char* dump = argc > 3 && std::string_view{argv[3]} != "-" ? argv[3] : nullptr;
+  const char* ttdb = argc > 4 ? argv[4] : "./particles.ttdb";
 
   constexpr Real H = 0.6;   // Water column height.
   constexpr Real L = 2 * H; // Water column length.
@@ -151,6 +155,17 @@ auto sph_main(int argc, char** argv) -> int {
   // Initialize the particles.
   equations.initialize(mesh, particles);
 
+  // Create a data storage to store the particles. We'll store only one last
+  // run result, all the previous runs will be discarded.
+  std::optional<data::Storage> storage;
+  std::optional<data::SeriesView<data::Storage>> series;
+  if (std::string_view{ttdb} != "-") {
+    storage.emplace(ttdb);
+    storage->set_max_series(1);
+    series = storage->create_series();
+    particles.write(0.0, *series);
+  }
+
   // Run the simulation.
   Real time{};
   const auto t0 = std::chrono::steady_clock::now();
@@ -168,6 +183,8 @@ auto sph_main(int argc, char** argv) -> int {
     if (output) {
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       std::printf("%15zu\t\t%10.5f\t\t%10.5f s/step\t\tdt = %.6e\n", step, double(scaled_time), el / double(step), double(dt));
+      // The frame time of the very first step would repeat the initial frame's.
+      if (series && scaled_time > series->last_frame().time()) particles.write(scaled_time, *series);
     }
 
     if (end) break;
