@@ -334,3 +334,73 @@ def test_facade_driver_writes_ttdb(tmp_path):
     assert list(last) == list(ttdb.PARTICLE_FIELDS) and last["L"].shape == (n, 2, 2)
     assert not first["v"].any() and last["v"].any()  # the initial frame is the state before the first step
     assert (last["gamma"] > 0).all() and np.isfinite(last["dv_dt"]).all() and last["dv_dt"].any()
+
+
+# ---------------------------------------------------------------- the 3-D driver
+def _driver_3d():
+    import __graft_entry__ as ge
+
+    return os.path.join(os.path.dirname(ge.build_examples()), "wcsph3d")
+
+
+def test_cpp_3d_driver_setup_matches_python_case(tmp_path):
+    """examples/wcsph3d.cpp builds the same tank as titsolver_b200.cases.dam_break_3d:
+    wall and containment surfaces bit-identical, fluid within the jitter of the lattice."""
+    from titsolver_b200 import cases
+
+    db = tmp_path / "setup.ttdb"
+    out = subprocess.run([_driver_3d(), "-5", "0", str(db), "0.93", "0.1"], capture_output=True, text=True)
+    assert out.returncode == 0 and "200 fluid + 1890 fixed" in out.stdout, (out.stdout, out.stderr)
+    with ttdb.Storage(str(db), read_only=True) as s:
+        d = s.last_series().last_frame().read()
+    c = cases.dam_break_3d(5, wall_ratio=0.93)
+    assert np.array_equal(d["verts"], c.verts) and np.array_equal(d["faces"], c.faces)
+    assert np.array_equal(d["containment_verts"], c.cverts) and np.array_equal(d["containment_faces"], c.cfaces)
+    nf = c.n_fluid
+    assert np.array_equal(d["r"][nf:], c.verts) and np.array_equal(d["m"], c.m) and np.array_equal(d["rho"][nf:], c.rho[nf:])
+    off = np.abs(d["r"][:nf] - c.r[:nf]) / c.dr
+    assert 0.05 < off.max() <= 0.1 and off.min() < 0.01
+    assert np.allclose(d["rho"][:nf], c.rho0 + c.rho0 * c.g * (c.H - d["r"][:nf, 1]) / c.cs0**2, rtol=1e-15)
+    # without jitter the lattice itself
+    out = subprocess.run([_driver_3d(), "-4", "0", str(tmp_path / "s4.ttdb")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    with ttdb.Storage(str(tmp_path / "s4.ttdb"), read_only=True) as s:
+        d4 = s.last_series().last_frame().read()
+    c4 = cases.dam_break_3d(4)
+    assert np.array_equal(d4["r"], c4.r) and np.array_equal(d4["rho"], c4.rho) and np.array_equal(d4["faces"], c4.faces)
+
+
+@pytest.mark.gpu
+def test_cpp_3d_driver_matches_python_solver_and_oracle(oracle, tmp_path):
+    """Three SSPRK3 steps of the 3-D dam break through the C++ facade against the
+    Python binding (same library: same bits) and against the oracle, both fed the
+    particles of the driver's initial frame."""
+    import dataclasses
+
+    import titsolver_b200 as tb
+
+    db = tmp_path / "run.ttdb"
+    out = subprocess.run([_driver_3d(), "5", "3", str(db), "0.93", "0.1"], capture_output=True, text=True)
+    assert out.returncode == 0, (out.stdout, out.stderr)
+    with ttdb.Storage(str(db), read_only=True) as s:
+        series = s.last_series()
+        assert series.num_frames == 2
+        first, last = series.frame(0).read(), series.frame(1).read()
+    case = dataclasses.replace(tb.cases.dam_break_3d(5, wall_ratio=0.93), r=first["r"], rho=first["rho"], m=np.full_like(first["m"], 1000.0 * (0.6 / 5) ** 3))
+    nf = case.n_fluid
+    assert np.array_equal(first["r"][nf:], case.verts)
+    # initialize() scales the wall masses by gamma (fluid_equations.hpp:88); the frame holds the scaled ones
+    assert np.array_equal(first["m"][:nf], case.m[:nf]) and (first["m"][nf:] <= case.m[nf:]).all()
+    gpu = tb.Solver(3)
+    tb.load_case(gpu, case)
+    gpu.initialize()
+    gpu.step(3)
+    cpu = oracle.OracleSolver(3)
+    oracle.load_case(cpu, case)
+    cpu.initialize()
+    cpu.step(3)
+    for f, tol_same, tol_oracle in (("r", 1e-14, 1e-10), ("v", 1e-12, 1e-7), ("rho", 1e-14, 1e-10)):
+        same, ref = gpu.download(f), cpu.download(f)
+        assert np.abs(last[f] - same).max() <= tol_same * np.abs(same).max(), f
+        assert np.abs(last[f][:nf] - ref[:nf]).max() <= tol_oracle * np.abs(ref[:nf]).max(), f
+    assert last["L"].shape == (case.n, 3, 3) and last["v"][:nf].any()
