@@ -201,10 +201,28 @@ template<class Num> struct GridSearch final { Num size_hint; };
 template<class Num> GridSearch(Num) -> GridSearch<Num>;
 template<class Num> struct GridFaceSearch final { Num size_hint; };
 template<class Num> GridFaceSearch(Num) -> GridFaceSearch<Num>;
+/// K-d tree index option (search/kd_tree_search.hpp:129-142): same contract as the grid
+/// index; on the GPU either is served by the spatial hash (identical neighbour rows,
+/// tests/test_gpu_parity.py::test_neighbors_match_kd_tree_index).
 struct KDTreeSearch final {};
+inline constexpr KDTreeSearch kd_tree_indexing{};
+/// Partitioners (partition/recursive_bisection.hpp:102-113, sort_partition.hpp:82-93,
+/// kmeans_clustering.hpp:30-138): they colour pairs for the CPU thread pool; the
+/// gather-form GPU pair sums need no colouring, so the options are accepted and unused.
 struct RecursiveInertialBisection final {};
 struct RecursiveCoordBisection final {};
-struct KMeansClustering final {};
+struct HilbertCurvePartition final {};
+struct MortonCurvePartition final {};
+struct KMeansClustering final {
+  constexpr explicit KMeansClustering(float64_t eps = 1.0e-4, std::size_t max_iter = 10) noexcept : eps{eps}, max_iter{max_iter} {}
+  float64_t eps;
+  std::size_t max_iter;
+};
+inline constexpr RecursiveInertialBisection recursive_inertial_bisection{};
+inline constexpr RecursiveCoordBisection recursive_coord_bisection{};
+inline constexpr HilbertCurvePartition hilbert_curve_partition{};
+inline constexpr MortonCurvePartition morton_curve_partition{};
+inline constexpr KMeansClustering kmeans_clustering{};
 template<class Num, class Clustering = KMeansClustering> struct PixelatedPartition final { Num size_hint; Clustering clustering{}; };
 template<class Num, class C> PixelatedPartition(Num, C) -> PixelatedPartition<Num, C>;
 

@@ -245,6 +245,31 @@ int orc_grid_cells_intersecting(int dim, const double* lo, const double* hi, dou
   };
   return dim == 2 ? run(std::integral_constant<int, 2>{}) : run(std::integral_constant<int, 3>{});
 }
+// Neighbour rows through the K-d tree index (kd_tree_search.hpp) as ParticleMesh::search_
+// builds them (particle_mesh.hpp:137-147: every point's own sphere, rows sorted).
+int orc_kdtree_neighbors(int dim, const double* pts, size_t n, double radius, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz) {
+  auto run = [&](auto g) {
+    constexpr int D = decltype(g)::value;
+    std::vector<Vec<D>> p(n);
+    for (size_t i = 0; i < n; ++i) p[i] = ld<D>(pts + i * D);
+    const KDTree<D> tree(p);
+    std::vector<uint64_t> row;
+    size_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+      row.clear();
+      BSphere<D> s; s.c = p[i]; s.r = radius;
+      tree.search(s, [&](size_t j) { row.push_back(j); });
+      std::sort(row.begin(), row.end());
+      if (cols && total + row.size() <= cap) std::memcpy(cols + total, row.data(), row.size() * 8);
+      if (off) off[i] = total;
+      total += row.size();
+    }
+    if (off) off[n] = total;
+    *nnz = total;
+    return cols && total > cap ? 2 : 0;
+  };
+  return dim == 2 ? run(std::integral_constant<int, 2>{}) : run(std::integral_constant<int, 3>{});
+}
 int orc_lu_inverse(int dim, const double* A, double* inv) {
   if (dim == 2) { Mat<2> a, r; std::memcpy(&a, A, sizeof a); if (!lu_inverse(a, r)) return 1; std::memcpy(inv, &r, sizeof r); return 0; }
   Mat<3> a, r; std::memcpy(&a, A, sizeof a); if (!lu_inverse(a, r)) return 1; std::memcpy(inv, &r, sizeof r); return 0;

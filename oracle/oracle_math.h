@@ -222,6 +222,59 @@ template<int D> struct Grid {
   }
 };
 
+// geom/search/kd_tree_search.hpp:33-142: the alternative search index (same contract
+// as the grid index). Median split along the longest axis of the bounding box of the
+// node's points (bipartition.hpp:101-125: nth_element on that coordinate; the median
+// point stays in the node), recursive sphere query that always descends to the side
+// of the centre and to the other side only if the splitting plane is strictly closer
+// than the radius (:113-121). The reference allocates nodes from parallel tasks, so
+// its node numbering is not defined; this one numbers them in depth-first order.
+template<int D> struct KDTree {
+  static constexpr std::size_t npos = std::numeric_limits<std::size_t>::max();
+  struct Node { std::size_t index = 0, axis = 0, left = npos, right = npos; };
+  const std::vector<Vec<D>>* pts = nullptr;
+  std::vector<Node> nodes;
+
+  explicit KDTree(const std::vector<Vec<D>>& points) : pts(&points) {
+    if (points.empty()) return;
+    std::vector<std::size_t> perm(points.size());
+    for (std::size_t i = 0; i < perm.size(); ++i) perm[i] = i;
+    nodes.reserve(points.size());
+    build(perm.data(), perm.size());
+  }
+  std::size_t build(std::size_t* perm, std::size_t n) {
+    const std::size_t id = nodes.size();
+    nodes.emplace_back();
+    if (n == 1) { nodes[id].index = perm[0]; return id; }
+    BBox<D> box((*pts)[perm[0]]);
+    for (std::size_t k = 1; k < n; ++k) box.expand((*pts)[perm[k]]);
+    const Vec<D> e = box.extents();
+    std::size_t axis = 0;  // max_value_index: the first of equal maxima
+    for (int i = 1; i < D; ++i) if (e[i] > e[axis]) axis = i;
+    const std::size_t med = n / 2;
+    std::nth_element(perm, perm + med, perm + n, [&](std::size_t a, std::size_t b) { return (*pts)[a][axis] < (*pts)[b][axis]; });
+    nodes[id].axis = axis;
+    nodes[id].index = perm[med];
+    if (med > 0) { const std::size_t l = build(perm, med); nodes[id].left = l; }
+    if (n - med > 1) { const std::size_t r = build(perm + med + 1, n - med - 1); nodes[id].right = r; }
+    return id;
+  }
+  template<class Out> void search(const BSphere<D>& s, Out&& out, std::size_t node = 0) const {
+    if (node == npos || nodes.empty()) return;
+    const Node& nd = nodes[node];
+    const Vec<D>& p = (*pts)[nd.index];
+    if (s.contains(p)) out(nd.index);
+    const double delta = s.c[nd.axis] - p[nd.axis];
+    if (delta < 0.0) {
+      search(s, out, nd.left);
+      if (pow2(delta) < pow2(s.r)) search(s, out, nd.right);
+    } else {
+      search(s, out, nd.right);
+      if (pow2(delta) < pow2(s.r)) search(s, out, nd.left);
+    }
+  }
+};
+
 // geom/segment.hpp.
 struct Segment {
   Vec<2> a, b;

@@ -50,6 +50,7 @@ def load(fast: bool = False) -> C.CDLL:
     lib.orc_step.argtypes = [vp, C.c_int, dp]
     lib.orc_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
     lib.orc_face_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
+    lib.orc_kdtree_neighbors.argtypes = [C.c_int, dp, sz, d, u64p, u64p, sz, C.POINTER(sz)]
     lib.orc_set_num_threads.argtypes = [C.c_int]
     lib.orc_tiny.restype = d
     lib.orc_kernel_radius.restype = d
@@ -168,6 +169,20 @@ class OracleSolver:
 
     def face_neighbors(self):
         return self._csr(self.lib.orc_face_neighbors)
+
+
+def kdtree_neighbors(pts, radius):
+    """Sorted neighbour rows (CSR) through the oracle's K-d tree index
+    (geom/search/kd_tree_search.hpp restated in oracle_math.h)."""
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    n, dim = pts.shape
+    lib = load()
+    nnz = C.c_size_t(0)
+    assert lib.orc_kdtree_neighbors(dim, _dp(pts), n, radius, None, None, 0, C.byref(nnz)) == 0
+    off = np.zeros(n + 1, np.uint64)
+    cols = np.zeros(max(nnz.value, 1), np.uint64)
+    assert lib.orc_kdtree_neighbors(dim, _dp(pts), n, radius, _u64p(off), _u64p(cols), nnz.value, C.byref(nnz)) == 0
+    return off, cols[: nnz.value]
 
 
 def load_case(solver, case):

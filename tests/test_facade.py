@@ -27,7 +27,17 @@ def test_facade_driver_compiles_and_links():
 @pytest.mark.parametrize("std", ["c++20", "c++23"])
 def test_facade_header_standalone(std, tmp_path):
     src = tmp_path / "t.cpp"
-    src.write_text('#include "tit_b200/sph.hpp"\nint main() { tit::Vec v{1.0, 2.0}; return int(tit::dot(v, v)) - 5; }\n')
+    src.write_text('''#include "tit_b200/sph.hpp"
+int main() {
+  using namespace tit;
+  // the alternative index / partition options of the reference are accepted (SURVEY §8a-a5, a7)
+  sph::ParticleMesh kd{geom::KDTreeSearch{}, geom::GridFaceSearch{0.1}, geom::RecursiveCoordBisection{}, geom::KMeansClustering{1e-3, 5}};
+  sph::ParticleMesh sorted{geom::kd_tree_indexing, geom::GridFaceSearch{0.1}, geom::hilbert_curve_partition, geom::PixelatedPartition{0.2, geom::kmeans_clustering}};
+  if (kd.search_hint() != 0.0 || sorted.face_search_hint() != 0.1) return 1;
+  Vec v{1.0, 2.0};
+  return int(dot(v, v)) - 5;
+}
+''')
     subprocess.check_call(["/usr/bin/g++", f"-std={std}", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", f"-I{ROOT}/include", str(src)])
 
 

@@ -57,6 +57,23 @@ def test_neighbors_random_cloud(oracle, dim, radius):
         assert set(cols[off[a]:off[a + 1]].tolist()) >= set(np.nonzero(d2 < (radius * (1 - 1e-12)) ** 2)[0].tolist())
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_neighbors_match_kd_tree_index(oracle, dim):
+    """SURVEY §8a-a5: `geom::KDTreeSearch` is the reference's alternative index with the
+    grid index's contract (search.test.cpp:122-125). On the GPU either option is served
+    by the spatial hash; its rows equal the K-d tree's (oracle restatement) bit for bit."""
+    rng = np.random.default_rng(321)
+    pts = rng.uniform(0.0, 1.0, size=(3000, dim))
+    empty_v, empty_f = np.zeros((0, dim)), np.zeros((0, dim), np.uint64)
+    for radius in (0.02, 0.15):
+        s = tb.Solver(dim, 0)
+        s.set_params(9.81, 1e-3, 10.0, 1000.0, 7.0, radius / 2.0)
+        s.set_surface(empty_v, empty_f, empty_v, empty_f)
+        s.set_particles(len(pts), 0)
+        s.upload("r", pts)
+        assert_csr_equal(s.neighbors(), oracle.kdtree_neighbors(pts, radius))
+
+
 @pytest.mark.parametrize("n_col", [20, 80])
 def test_neighbors_dam_break_lattice(oracle, n_col):
     """The lattice puts neighbours at exactly 4 dr = 2h with an inclusive test."""

@@ -86,6 +86,42 @@ def test_grid_search_matches_brute_force(dim, radius, scale):
         assert np.all(np.diff(row.astype(np.int64)) > 0)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("radius", [0.01, 0.1, 0.5, 1.0])
+def test_kd_tree_search_matches_brute_force(dim, radius):
+    """geom/search.test.cpp:122-125: the K-d tree index on the same clouds."""
+    pts = reference_cloud(dim)
+    off, cols = ol.kdtree_neighbors(pts, radius)
+    assert csr_rows(off, cols) == brute_neighbors(pts, radius)
+    # ... and identical, row by row, to the grid index (both feed ParticleMesh::search_)
+    goff, gcols = oracle_search(pts, radius, radius, dim)
+    assert np.array_equal(off, goff) and np.array_equal(cols, gcols)
+
+
+def test_kd_tree_search_empty_single_and_duplicates():
+    off, cols = ol.kdtree_neighbors(np.zeros((0, 2)), 0.1)
+    assert len(cols) == 0 and list(off) == [0]
+    off, cols = ol.kdtree_neighbors(np.array([[0.3, 0.4, 0.5]]), 0.1)
+    assert list(off) == [0, 1] and list(cols) == [0]
+    # Coincident points, and points exactly one radius apart. The point test is inclusive
+    # (bsphere.hpp:52-53) but the descent to the far side of a splitting plane is strict
+    # (kd_tree_search.hpp:116-120: pow2(delta) < pow2(radius)), so a point exactly one radius
+    # away along the split axis may or may not be reported, depending on where the tree was
+    # split: every row lies between the strict and the inclusive brute-force answer. (The
+    # grid index, and the GPU hash behind either option, always give the inclusive answer.)
+    pts = np.array([[0.0, 0.0], [0.0, 0.0], [0.5, 0.0], [1.0, 0.0], [0.0, 0.5], [0.0, 0.0]])
+    off, cols = ol.kdtree_neighbors(pts, 0.5)
+    rows = csr_rows(off, cols)
+    d2 = ((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)
+    for i, row in enumerate(rows):
+        strict = set(np.nonzero(d2[i] < 0.25)[0].tolist())
+        inclusive = set(np.nonzero(d2[i] <= 0.25)[0].tolist())
+        assert strict <= row <= inclusive, (i, row)
+    assert rows[0] == {0, 1, 2, 4, 5} and rows[3] == {2, 3}
+    goff, gcols = oracle_search(pts, 0.5, 0.5, 2)
+    assert csr_rows(goff, gcols) == [set(np.nonzero(d2[i] <= 0.25)[0].tolist()) for i in range(len(pts))]
+
+
 def test_grid_search_empty():
     off, cols = oracle_search(np.zeros((0, 2)), 0.1, 0.05, 2)
     assert len(cols) == 0 and list(off) == [0]
