@@ -404,3 +404,77 @@ def test_cpp_3d_driver_matches_python_solver_and_oracle(oracle, tmp_path):
         assert np.abs(last[f] - same).max() <= tol_same * np.abs(same).max(), f
         assert np.abs(last[f][:nf] - ref[:nf]).max() <= tol_oracle * np.abs(ref[:nf]).max(), f
     assert last["L"].shape == (case.n, 3, 3) and last["v"][:nf].any()
+
+
+# ---------------------------------------------------------------- ParaView export
+def _check_xdmf(xdmf_path, series):
+    import xml.etree.ElementTree as ET
+
+    root = ET.parse(xdmf_path).getroot()
+    assert root.tag == "Xdmf" and root.get("Version") == "3.0"
+    (domain,) = list(root)
+    (collection,) = list(domain)
+    assert (collection.get("Name"), collection.get("GridType"), collection.get("CollectionType")) == ("TimeSeries", "Collection", "Temporal")
+    frames = series.frames()
+    grids = list(collection)
+    assert len(grids) == len(frames)
+    heavy = open(os.path.join(os.path.dirname(xdmf_path), "particles.bin"), "rb").read()
+
+    def load(item):
+        assert item.get("Format") == "Binary" and item.get("Endian") == "Little" and item.text == "particles.bin"
+        shape = tuple(int(d) for d in item.get("Dimensions").split())
+        dt = np.dtype({"Float": "f", "Int": "i"}[item.get("NumberType")] + item.get("Precision"))
+        return np.frombuffer(heavy, dtype=dt, count=int(np.prod(shape)), offset=int(item.get("Seek"))).reshape(shape)
+
+    width = len(str(len(frames) - 1)) if len(frames) > 1 else 1
+    for index, (grid, frame) in enumerate(zip(grids, frames)):
+        assert grid.get("GridType") == "Uniform" and grid.get("Name") == f"frame-{index:0{width}d}"
+        data = frame.read()
+        kids = list(grid)
+        assert [k.tag for k in kids[:3]] == ["Time", "Topology", "Geometry"]
+        assert float(kids[0].get("Value")) == frame.time
+        assert kids[1].get("TopologyType") == "Polyvertex" and int(kids[1].get("NumberOfElements")) == data["r"].shape[0]
+        assert kids[2].get("GeometryType") == {2: "XY", 3: "XYZ"}[data["r"].shape[1]]
+        assert np.array_equal(load(kids[2][0]), data["r"])
+        exported = [a for a in frame.arrays() if data[a.name].ndim < 3]  # matrices are skipped (hdf5.cpp:178-181)
+        attrs = kids[3:]
+        assert [a.get("Name") for a in attrs] == [a.name for a in exported]
+        for attr in attrs:
+            want = data[attr.get("Name")]
+            assert attr.get("Center") == "Node" and attr.get("AttributeType") == ("Scalar" if want.ndim == 1 else "Vector")
+            got = load(attr[0])
+            assert got.shape == want.shape and np.array_equal(got.view(want.dtype) if got.dtype != want.dtype else got, want)
+
+
+@pytest.mark.parametrize("dim, n_frames", [(2, 1), (3, 3), (2, 11)])
+def test_xdmf_export(tmp_path, dim, n_frames):
+    from titsolver_b200 import xdmf
+
+    rng = np.random.default_rng(5)
+    s = ttdb.Storage()
+    series = s.create_series()
+    for k in range(n_frames):
+        n = 20 + k
+        fields = {"r": rng.normal(size=(n, dim)), "rho": rng.normal(size=n), "v": rng.normal(size=(n, dim)), "L": rng.normal(size=(n, dim, dim)),
+                  "parinfo": np.arange(n, dtype=np.uint64)}
+        series.write_particles(0.5 * k, fields, names=["rho", "r", "L", "v", "parinfo"])
+    out = xdmf.export_xdmf(str(tmp_path), series)
+    assert os.path.basename(out) == "particles.xdmf"
+    _check_xdmf(out, series)
+    with pytest.raises(FileNotFoundError, match="Directory does not exist"):
+        xdmf.export_xdmf(str(tmp_path / "nope"), series)
+    with pytest.raises(NotADirectoryError, match="not a directory"):
+        xdmf.export_xdmf(out, series)
+    empty = s.create_series().create_frame(0.0)
+    empty.create_array("rho").write(np.zeros(3))
+    with pytest.raises(KeyError, match="'r' not found"):
+        xdmf.export_xdmf(str(tmp_path), s.last_series())
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FIXTURE), reason="the reference tree is only present in the build container")
+def test_xdmf_export_of_the_reference_fixture(tmp_path):
+    from titsolver_b200 import xdmf
+
+    with ttdb.Storage(REF_FIXTURE, read_only=True) as s:
+        series = s.last_series()
+        _check_xdmf(xdmf.export_xdmf(str(tmp_path), series), series)
