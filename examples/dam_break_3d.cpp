@@ -20,7 +20,7 @@
 // and the parity tests); tests/test_ttdb.py checks that both give the same mesh
 // and, fed the same particles, the same result.
 //
-//   wcsph3d [n_col=16] [max_steps=0 (run to t sqrt(g/H) = 10)] [particles.ttdb|-] [wall_ratio=1] [jitter=0]
+//   dam_break_3d [n_col=16] [max_steps=0 (run to t sqrt(g/H) = 10)] [particles.ttdb|-] [wall_ratio=1] [jitter=0]
 // A negative n_col writes only the set-up of |n_col| (surfaces and initial
 // particles, one frame) and stops before the first GPU call.
 #include <array>
@@ -38,7 +38,7 @@
 
 #include "tit_b200/sph.hpp"
 
-namespace tit::sph::wcsph3d {
+namespace tit::sph::dam_break_3d {
 namespace {
 
 using Real = float64_t;
@@ -250,12 +250,12 @@ auto sph_main(int argc, char** argv) -> int {
 }
 
 } // namespace
-} // namespace tit::sph::wcsph3d
+} // namespace tit::sph::dam_break_3d
 
 int main(int argc, char** argv) {
   try {
     tit::par::init();
-    return tit::sph::wcsph3d::sph_main(argc, argv);
+    return tit::sph::dam_break_3d::sph_main(argc, argv);
   } catch (const tit::Exception& e) {
     std::fprintf(stderr, "ERROR: %s\n", e.what());
     return 1;

@@ -3,7 +3,7 @@
 // Keeps the names, call order and argument meaning of the reference's
 // header-only template API for the WCSPH particle step, so that
 // /root/reference/source/titwcsph/wcsph.cpp compiles nearly verbatim against
-// the B200 library (see examples/wcsph.cpp and INTEGRATION.md):
+// the B200 library (see examples/dam_break_2d.cpp and INTEGRATION.md):
 //
 //   tit::Vec, tit::Mat                              tit/core/vec.hpp, mat.hpp (the subset the driver uses)
 //   tit::geom::Surface, tessellate (2-D, 3-D)       tit/geom/surface.hpp, tessellation.hpp:30-63, 74-163

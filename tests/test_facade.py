@@ -43,7 +43,7 @@ int main() {
 
 @pytest.mark.gpu
 def test_facade_driver_matches_oracle(oracle, tmp_path):
-    """examples/wcsph.cpp (the reference's wcsph.cpp against the facade) for 5 steps
+    """examples/dam_break_2d.cpp (the reference's default case through the facade) for 5 steps
     of the 2-D dam break vs the oracle fed by the Python case generator."""
     from titsolver_b200 import cases
 
@@ -88,3 +88,19 @@ int main() {
     subprocess.check_call(["/usr/bin/g++", "-std=c++20", f"-I{ROOT}/include", str(src), "-o", str(exe), f"-L{ROOT}/titsolver_b200", "-ltitgpu", f"-Wl,-rpath,{ROOT}/titsolver_b200"])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "caught: " in r.stdout, (r.stdout, r.stderr)
+
+
+def test_facade_2d_driver_setup_matches_python_case(tmp_path):
+    """examples/dam_break_2d.cpp sets up the reference's default case exactly as
+    titsolver_b200.cases.dam_break_2d does (the case the oracle and the GPU tests use)."""
+    from titsolver_b200 import cases, ttdb
+
+    db = tmp_path / "setup.ttdb"
+    out = subprocess.run([build_example(), "-20", "0", "-", str(db)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.stdout, out.stderr)
+    with ttdb.Storage(str(db), read_only=True) as s:
+        d = s.last_series().last_frame().read()
+    c = cases.dam_break_2d(20)
+    assert f"{c.n_fluid} fluid + {c.n_fixed} fixed" in out.stdout
+    for got, want in (("verts", c.verts), ("faces", c.faces), ("containment_verts", c.cverts), ("containment_faces", c.cfaces), ("r", c.r), ("m", c.m), ("rho", c.rho)):
+        assert np.array_equal(d[got], want), got

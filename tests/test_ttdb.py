@@ -316,7 +316,7 @@ def test_solver_frames_roundtrip(tmp_path):
 
 @pytest.mark.gpu
 def test_facade_driver_writes_ttdb(tmp_path):
-    """examples/wcsph.cpp with the reference's storage calls: the last frame of the
+    """examples/dam_break_2d.cpp with the reference's storage calls: the last frame of the
     database equals the raw dump of the final state."""
     import __graft_entry__ as ge
 
@@ -340,11 +340,11 @@ def test_facade_driver_writes_ttdb(tmp_path):
 def _driver_3d():
     import __graft_entry__ as ge
 
-    return os.path.join(os.path.dirname(ge.build_examples()), "wcsph3d")
+    return os.path.join(os.path.dirname(ge.build_examples()), "dam_break_3d")
 
 
 def test_cpp_3d_driver_setup_matches_python_case(tmp_path):
-    """examples/wcsph3d.cpp builds the same tank as titsolver_b200.cases.dam_break_3d:
+    """examples/dam_break_3d.cpp builds the same tank as titsolver_b200.cases.dam_break_3d:
     wall and containment surfaces bit-identical, fluid within the jitter of the lattice."""
     from titsolver_b200 import cases
 

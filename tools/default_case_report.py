@@ -1,5 +1,5 @@
 """Physical sanity report of a dam-break run stored in a `.ttdb` database
-(examples/wcsph.cpp or wcsph3d.cpp, i.e. the reference's default case on the GPU path).
+(examples/dam_break_2d.cpp or dam_break_3d.cpp, i.e. the reference's default case on the GPU path).
 
     python tools/default_case_report.py particles.ttdb report.json [thin.ttdb]
 
