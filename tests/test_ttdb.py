@@ -478,3 +478,46 @@ def test_xdmf_export_of_the_reference_fixture(tmp_path):
     with ttdb.Storage(REF_FIXTURE, read_only=True) as s:
         series = s.last_series()
         _check_xdmf(xdmf.export_xdmf(str(tmp_path), series), series)
+
+
+# ---------------------------------------------------------------- python -m titsolver_b200
+def test_cli_arguments_and_no_cpu_fallback():
+    from titsolver_b200 import __main__ as cli
+
+    a = cli.parse(["--dim", "3", "--n-col", "16", "--max-steps", "7", "--kernel", "cubic", "--integrator", "verlet"])
+    assert (a.dim, a.n_col, a.max_steps, a.frame_every, a.end_time, a.out) == (3, 16, 7, 100, 10.0, "particles.ttdb")
+    assert cli.KERNELS.index(a.kernel) == 0 and cli.INTEGRATORS.index(a.integrator) == 1
+    assert cli.KERNELS.index("wendland6") == 4 and cli.INTEGRATORS.index("ssprk3") == 3  # TITGPU_* ids of include/titgpu.h
+    for bad in (["--n-col", "1"], ["--xdmf", "d", "--out", "-"], ["--dim", "1"]):
+        with pytest.raises(SystemExit):
+            cli.parse(bad)
+    import torch
+
+    if not torch.cuda.is_available():  # the product path fails loudly without a GPU
+        import titsolver_b200 as tb
+
+        with pytest.raises(tb.TitGpuError):
+            cli.main(["--n-col", "10", "--max-steps", "2", "--out", "-"])
+
+
+@pytest.mark.gpu
+def test_cli_run_matches_direct_solver(tmp_path):
+    import titsolver_b200 as tb
+    from titsolver_b200 import __main__ as cli
+
+    db, out = tmp_path / "particles.ttdb", tmp_path / "paraview"
+    out.mkdir()
+    assert cli.main(["--n-col", "20", "--max-steps", "5", "--frame-every", "2", "--out", str(db), "--xdmf", str(out)]) == 0
+    case = tb.cases.dam_break_2d(20)
+    gpu = tb.Solver(2)
+    tb.load_case(gpu, case)
+    gpu.initialize()
+    for _ in range(5):
+        gpu.step(1)
+    with ttdb.Storage(str(db), read_only=True) as s:
+        series = s.last_series()
+        assert series.num_frames == 4  # initial, steps 2 and 4, the last step
+        last = series.last_frame().read()
+        for f in ("r", "v", "rho", "dv_dt", "L", "gamma"):
+            assert np.array_equal(last[f], gpu.download(f)), f
+        _check_xdmf(str(out / "particles.xdmf"), series)

@@ -1,7 +1,7 @@
 """titsolver_b200 — B200-native WCSPH particle step behind the TitSolver API.
 
 The product is `libtitgpu.so` (hand-written sm_100a CUDA kernels + a C ABI,
-see include/titgpu.h) and the C++ facade in include/tit/. This module is the
+see include/titgpu.h) and the C++ facade in include/tit_b200/. This module is the
 thin ctypes binding used by the tests and bench.py; it mirrors the call
 sequence of /root/reference/source/titwcsph/wcsph.cpp.
 

@@ -19,7 +19,9 @@ from __future__ import annotations
 
 import ctypes
 import ctypes.util
+import os
 import sqlite3
+import urllib.parse
 from typing import Iterable
 
 import numpy as np
@@ -325,7 +327,7 @@ class Storage:
     def __init__(self, path: str = ":memory:", read_only: bool = False):
         self.read_only = read_only
         if read_only:
-            self._db = sqlite3.connect(f"file:{path}?mode=ro", uri=True)
+            self._db = sqlite3.connect(f"file:{urllib.parse.quote(os.path.abspath(str(path)))}?mode=ro", uri=True)
             self._db.execute("SELECT COUNT(*) FROM sqlite_master").fetchone()
         else:
             self._db = sqlite3.connect(str(path))
