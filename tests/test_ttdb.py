@@ -521,3 +521,38 @@ def test_cli_run_matches_direct_solver(tmp_path):
         for f in ("r", "v", "rho", "dv_dt", "L", "gamma"):
             assert np.array_equal(last[f], gpu.download(f)), f
         _check_xdmf(str(out / "particles.xdmf"), series)
+
+
+def test_cpp_xdmf_export(tmp_path):
+    """include/tit_b200/xdmf.hpp writes the same document as titsolver_b200/xdmf.py."""
+    rng = np.random.default_rng(11)
+    db = tmp_path / "run.ttdb"
+    with ttdb.Storage(str(db)) as s:
+        series = s.create_series("a <run> & more")
+        for k in range(12):
+            n = 30 + k
+            fields = {"rho": rng.normal(size=n), "r": rng.normal(size=(n, 3)), "L": rng.normal(size=(n, 3, 3)), "v": rng.normal(size=(n, 3)),
+                      "parinfo": np.arange(n, dtype=np.uint64), "kind": np.arange(n, dtype=np.int8)}
+            series.write_particles(0.1 * k * np.pi, fields, names=list(fields))
+    src = tmp_path / "export.cpp"
+    src.write_text('''#include <cstdio>
+#include "tit_b200/xdmf.hpp"
+int main(int, char** argv) {
+  try {
+    const tit::data::Storage storage{argv[1], /*read_only=*/true};
+    const auto out = tit::data::export_xdmf(argv[2], storage.last_series());
+    std::printf("%s\\n", out.c_str());
+    try { tit::data::export_xdmf(out, storage.last_series()); return 2; } catch (const tit::Exception&) {}
+    try { tit::data::export_xdmf(std::string{argv[2]} + "/nope", storage.last_series()); return 3; } catch (const tit::Exception&) {}
+    return 0;
+  } catch (const std::exception& e) { std::fprintf(stderr, "%s\\n", e.what()); return 1; }
+}
+''')
+    exe, out_dir = tmp_path / "export", tmp_path / "paraview"
+    out_dir.mkdir()
+    subprocess.check_call(["/usr/bin/g++", "-std=c++20", "-Wall", "-Wextra", "-Werror", f"-I{ROOT}/include", str(src), "-o", str(exe), "-ldl"])
+    run = subprocess.run([str(exe), str(db), str(out_dir)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.stdout, run.stderr)
+    assert run.stdout.strip() == str(out_dir / "particles.xdmf")
+    with ttdb.Storage(str(db), read_only=True) as s:
+        _check_xdmf(str(out_dir / "particles.xdmf"), s.last_series())
