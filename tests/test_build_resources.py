@@ -1,0 +1,76 @@
+"""Build-time guard of the kernels' resource budgets (no GPU needed).
+
+DESIGN.md §3 states the register budgets as measured choices: the pair passes run at 64
+registers x 32 warps per SM with their a-side state in shared memory and (almost) no
+spill slots, `k_shift_sums` at 128 x 16, `k_weval` spill-free. `cuobjdump -res-usage` on
+the cross-compiled sm_100a objects shows whether a change to the sources silently broke
+that (a few more registers halve the occupancy, spill slots take L1 from the gathers).
+"""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "titsolver_b200", "_build")
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="CUDA toolkit binaries not on PATH")
+
+
+def resources(obj):
+    """{demangled-ish kernel key: dict(REG, STACK, SHARED)} of one object file."""
+    if not os.path.exists(obj):
+        import titsolver_b200.build as b
+
+        b.build()
+    out = subprocess.run(["cuobjdump", "-res-usage", obj], capture_output=True, text=True, check=True).stdout
+    res, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        if name and "REG:" in line:
+            res[name] = {k: int(v) for k, v in re.findall(r"(REG|STACK|SHARED):(\d+)", line)}
+            name = None
+    return res
+
+
+def pick(res, fragment):
+    hits = {k: v for k, v in res.items() if fragment in k}
+    assert hits, fragment
+    return hits
+
+
+@pytest.mark.parametrize("dim, kid", [(3, 4), (2, 4), (3, 0)])
+def test_pair_pass_budgets(dim, kid):
+    res = resources(os.path.join(BUILD, f"inst_{dim}_{kid}.o"))
+    for name, r in pick(res, f"k_rhsILi{dim}ELi{kid}E").items():
+        assert r["REG"] <= 64, (name, r)  # 4 blocks of 8 warps per SM
+        assert r["STACK"] <= 64, (name, r)  # a handful of spilled scalars at most, never the pair-loop state
+        assert 0 < 4 * r["SHARED"] <= 100 * 1024, (name, r)  # 4 resident blocks; most of the 256 KB L1 / shared array stays L1 for the gathers
+    for name, r in pick(res, f"k_setup_boundaryILi{dim}ELi{kid}E").items():
+        assert r["REG"] <= 64 and r["STACK"] <= 64, (name, r)
+    for name, r in pick(res, f"k_shift_sumsILi{dim}ELi{kid}E").items():
+        assert r["REG"] <= 128, (name, r)  # 4 blocks of 4 warps
+    for name, r in pick(res, f"k_near_surfaceILi{dim}E").items():
+        assert r["REG"] <= 64 and r["STACK"] == 0, (name, r)
+
+
+def test_wall_pipeline_budgets():
+    res = resources(os.path.join(BUILD, "inst_3_4.o"))
+    for name, r in pick(res, "k_wevalILi4E").items():
+        assert r["REG"] <= 96 and r["STACK"] == 0, (name, r)  # FP64-heaviest kernel: spill-free
+    for name, r in pick(res, "k_wsearchILi").items():
+        assert r["REG"] <= 64 and r["SHARED"] <= 24 * 1024, (name, r)  # 8 blocks of 4 warps per SM
+    for name, r in pick(res, "k_wcombineILi").items():
+        assert r["REG"] <= 128 and r["STACK"] == 0, (name, r)
+
+
+def test_streaming_kernels_are_light():
+    res = resources(os.path.join(BUILD, "inst_3_4.o"))
+    for frag in ("k_cell_countILi3E", "k_reorderILi3E", "k_eosILi3E", "k_dt_reduceILi3E", "k_apply_shiftILi3E", "k_unsortILi3E", "k_sort_inILi3E", "k_scatter", "k_rank"):
+        for name, r in pick(res, frag).items():
+            assert r["REG"] <= 40 and r["STACK"] == 0 and r["SHARED"] == 0, (name, r)  # full occupancy, HBM-bound
