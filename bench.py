@@ -81,6 +81,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_pipes(dim):
+    """Pipe utilisation of k_rhs from the committed `ncu --set full` capture (profiles/ncu_traffic.json):
+    FP64 / FP32 (FMA) pipe and L1 data-pipe busy %, issue-slot utilisation."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get("k_rhs", {}).get(f"{dim}d")
+    except (OSError, ValueError):
+        return None
+    return rec.get("pipes") if rec else None
+
+
 def ncu_traffic(dim, n):
     """DRAM bytes (read + write) of one k_rhs launch over n particles, from the committed
     `ncu --set full` capture (profiles/ncu_traffic.json: bytes per particle measured at the
@@ -212,11 +224,146 @@ def run_reference(args, rank, world):
     emit(json.dumps(out))
 
 
-def run_ours(args, rank, local_rank, world):
-    import numpy as np
-    import torch
+def strong_reference():
+    """The committed single-GPU rate of the strong-scaling workload (C5), measured with
+    `bench.py --scaling strong --workload c5 --gpus 1` (profiles/strong_c5_1gpu.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "strong_c5_1gpu.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
 
-    import titsolver_b200 as tb
+
+class Runner:
+    """One workload on this rank's GPU: a whole case (world == 1 or `whole`) or one slab."""
+
+    def __init__(self, args, dim, n_col, rank, local_rank, world, mode):
+        import torch
+
+        import titsolver_b200 as tb
+
+        self.torch, self.world, self.rank, self.dim, self.mode = torch, world, rank, dim, mode
+        self.slab = None
+        if world > 1:
+            if dim != 3:
+                raise SystemExit("bench.py: the multi-GPU workload is the 3-D dam break (use --workload c3/c4/c5)")
+            from titsolver_b200 import cases
+            from titsolver_b200.slab import SlabSolver
+
+            case, edges, axis = cases.dam_break_3d_slab(n_col, world, rank, mode=mode)
+            self.slab = SlabSolver(case, rank, world, axis=axis, edges=edges, device=local_rank, local=True)
+            self.solver = self.slab.solver
+            self.n_fluid, self.n_fixed = case.meta["n_fluid_global"], case.meta["n_fixed_global"]
+        else:
+            case = make_case(dim, n_col)
+            self.solver = tb.Solver(dim, device=local_rank)
+            tb.load_case(self.solver, case)
+            self.n_fluid, self.n_fixed = case.n_fluid, case.n_fixed
+        self.n_total = self.n_fluid + self.n_fixed  # particles of the whole job
+        self.name = case.meta.get("name", "")
+        del case
+        self.solver.initialize()
+        self.stream = torch.cuda.ExternalStream(self.solver.stream, device=torch.device("cuda", local_rank))
+        self.local_rank = local_rank
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        self.torch.cuda.synchronize()
+        self.solver.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_steps(self, steps, warmup, profile=True):
+        """W untimed + K timed steps with the state resident in HBM; device time, max over ranks."""
+        torch, solver = self.torch, self.solver
+        for _ in range(warmup):
+            solver.step(1)
+        if profile:
+            solver.profile(True)
+            solver.profile_reset()
+        launches0 = solver.launch_count
+        sampler = ClockSampler(self.local_rank)
+        self.barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        solver.step(steps)
+        e1.record(self.stream)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        launches = solver.launch_count - launches0
+        prof = solver.profile_read() if profile else {}
+        if profile:
+            solver.profile(False)
+        ms = self.max_over_ranks(ms)
+        return ms, clocks, launches, prof
+
+    def e2e_steps(self, steps, warmup):
+        """K steps through the C ABI with HOST buffers: every step uploads the state from
+        pinned memory, steps, and downloads it again. Returns (ms, h2d bytes, d2h bytes)."""
+        torch, solver = self.torch, self.solver
+        if self.slab is None:
+            host = {f: torch.empty(solver._shape(f), dtype=torch.float64).pin_memory() for f in ("r", "v", "rho")}
+            for f in host:
+                solver.download_raw(f, host[f].data_ptr())
+            h2d = d2h = sum(h.numel() * 8 for h in host.values())
+
+            def e2e_step():
+                for f in ("r", "v", "rho"):
+                    solver.upload_raw(f, host[f].data_ptr())
+                solver.step(1)
+                for f in ("r", "v", "rho"):
+                    solver.download_raw(f, host[f].data_ptr())
+        else:
+            # Slab mode: the owned fluid records (r, rho | v, m: 64 B per particle) and their global
+            # ids travel host -> device before and device -> host after every step (titgpu_mg_upload_owned /
+            # titgpu_mg_download_owned); the ghosts are fetched from the neighbours inside the step.
+            cap = int(solver.mg_counts()[0] * 1.05) + 4096
+            hostA = torch.empty((cap, 4), dtype=torch.float64).pin_memory()
+            hostB = torch.empty((cap, 4), dtype=torch.float64).pin_memory()
+            hostG = torch.empty((cap,), dtype=torch.int64).pin_memory()
+            state = {"n": solver.mg_download_owned(hostA.data_ptr(), hostB.data_ptr(), hostG.data_ptr(), cap=cap)}
+            h2d = d2h = int(state["n"]) * 72
+
+            def e2e_step():
+                solver.mg_upload_owned(state["n"], hostA.data_ptr(), hostB.data_ptr(), hostG.data_ptr())
+                solver.step(1)
+                state["n"] = solver.mg_download_owned(hostA.data_ptr(), hostB.data_ptr(), hostG.data_ptr(), cap=cap)
+
+        # Between output frames the reference's time loop reads nothing but what the
+        # next step needs (wcsph.cpp:170-193): the e2e loop publishes the state only.
+        solver.set_outputs(0)
+        for _ in range(min(warmup, 3)):
+            e2e_step()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            e2e_step()
+        e1.record(self.stream)
+        self.barrier()
+        ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)  # host-side work counts too
+        solver.set_outputs(2)
+        return self.max_over_ranks(ms), h2d, d2h
+
+    def close(self):
+        self.solver.close()
+        self.slab = None
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
@@ -231,127 +378,17 @@ def run_ours(args, rank, local_rank, world):
     w = WORKLOADS[args.workload]
     dim = w["dim"]
     n_col = args.n_col or w["n_col"]
-    slab = None
-    if world > 1:
-        # Weak scaling: the 3-D tank is made `world` times deeper along z and cut into
-        # `world` slabs (one per GPU) with ghost layers exchanged over NCCL send/recv
-        # before every neighbour search (titsolver_b200/slab.py).
-        if dim != 3:
-            raise SystemExit("bench.py: the multi-GPU workload is the 3-D dam break (use --workload c3/c4/c5)")
-        from titsolver_b200 import cases
-        from titsolver_b200.slab import SlabSolver
+    strong_main = args.scaling == "strong"
+    mode = "strong_x" if strong_main else "weak_z"
+    run = Runner(args, dim, n_col, rank, local_rank, world, mode)
+    solver = run.solver
+    n_job, n_fluid, n_fixed = run.n_total, run.n_fluid, run.n_fixed  # particles of the whole job
+    n = n_job / world  # per GPU (wall particles of the halos are not counted twice)
 
-        case, edges = cases.dam_break_3d_slab(n_col, world, rank)
-        slab = SlabSolver(case, rank, world, axis=2, edges=edges, device=local_rank, local=True)
-        solver = slab.solver
-        n_global = case.meta["n_fluid_global"] + case.meta["n_fixed_global"]
-        n = n_global / world  # particles per GPU (wall particles of the halos are not counted twice)
-    else:
-        case = make_case(dim, n_col)
-        n = case.n
-        solver = tb.Solver(dim, device=local_rank)
-        tb.load_case(solver, case)
-    solver.initialize()
-    stream = torch.cuda.ExternalStream(solver.stream, device=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        solver.synchronize()
-
-    # ---- value: state resident in HBM ------------------------------------
-    for _ in range(args.warmup):
-        solver.step(1)
-    solver.profile(True)
-    solver.profile_reset()
-    launches0 = solver.launch_count
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    solver.step(args.steps)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
-    launches = solver.launch_count - launches0
-    prof = solver.profile_read()
-    solver.profile(False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * n * args.steps / (ms * 1e-3)
-
-    # ---- e2e: host buffers through the C ABI every step -----------------
-    if slab is None:
-        host = {f: torch.empty(solver._shape(f), dtype=torch.float64).pin_memory() for f in ("r", "v", "rho")}
-        for f in host:
-            solver.download_raw(f, host[f].data_ptr())
-        h2d = d2h = sum(h.numel() * 8 for h in host.values())
-
-        def e2e_step():
-            for f in ("r", "v", "rho"):
-                solver.upload_raw(f, host[f].data_ptr())
-            solver.step(1)
-            for f in ("r", "v", "rho"):
-                solver.download_raw(f, host[f].data_ptr())
-    else:
-        # Slab mode: the owned fluid records (r, rho | v, m: 64 B per particle) travel
-        # host -> device before and device -> host after every step.
-        cap = int(slab.solver.mg_counts()[0] * 1.05) + 4096
-        hostA = torch.empty((cap, 4), dtype=torch.float64).pin_memory()
-        hostB = torch.empty((cap, 4), dtype=torch.float64).pin_memory()
-        tdev = torch.device("cuda", local_rank)
-        state = {"n": 0}
-
-        def pull():
-            with torch.cuda.stream(stream):
-                rec, n_owned = slab._export(False)
-                hostA[:n_owned].copy_(rec[:n_owned, 0:4], non_blocking=True)
-                hostB[:n_owned].copy_(rec[:n_owned, 4:8], non_blocking=True)
-            solver.synchronize()
-            state["n"] = n_owned
-
-        def push():
-            k = state["n"]
-            with torch.cuda.stream(stream):
-                dA = hostA[:k].to(tdev, non_blocking=True)
-                dB = hostB[:k].to(tdev, non_blocking=True)
-                solver.mg_import(k, 0, dA.data_ptr(), dB.data_ptr())
-                slab.gid = slab.gid[:k]
-                slab._keep = [dA, dB]
-
-        pull()
-        h2d = d2h = int(state["n"]) * 64
-
-        def e2e_step():
-            push()
-            solver.step(1)
-            pull()
-
-    # Between output frames the reference's time loop reads nothing but what the
-    # next step needs (wcsph.cpp:170-193): the e2e loop publishes the state only.
-    solver.set_outputs(0)
-    for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record(stream)
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e2e_ms, wall_ms)  # host-side packing counts too
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e_value = world * n * args.steps / (e2e_ms * 1e-3)
+    ms, clocks, launches, prof = run.timed_steps(args.steps, args.warmup)
+    value = n_job * args.steps / (ms * 1e-3)
+    e2e_ms, h2d, d2h = run.e2e_steps(args.steps, args.warmup)
+    e2e_value = n_job * args.steps / (e2e_ms * 1e-3)
 
     # ---- roofline of the kernel-sum pass ---------------------------------
     hbm_peak, peak_src = measured_peaks()
@@ -364,28 +401,65 @@ def run_ours(args, rank, local_rank, world):
         cnt, tot = prof[rhs_name]
         avg_s = tot / cnt * 1e-3
         ach = alg_bytes_rhs(dim) * n / avg_s / 1e9
-        flops = alg_flops_rhs(dim) * (case.n_fluid if slab is None else case.meta["n_fluid_global"] / world) / avg_s / 1e12
+        flops = alg_flops_rhs(dim) * (n_fluid / world) / avg_s / 1e12
+        traffic, traffic_src = ncu_traffic(dim, n)
         roof = {
-            "bound": "hbm", "kernel": rhs_name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic(dim, n)[0], "traffic_unit": "bytes per launch (DRAM read + write)",
-            "traffic_source": ncu_traffic(dim, n)[1],
-            "peak_source": peak_src, "alg_bytes_per_particle": alg_bytes_rhs(dim), "launches": cnt, "avg_ms": avg_s * 1e3,
+            # The kernel-sum pass is bound by the FP64 pipe / instruction issue, not by HBM: its
+            # algorithmic intensity is ~180 flop per compulsory byte. The HBM
+            # figure BASELINE.json asks for is reported beside it.
+            "bound": "fp64", "kernel": rhs_name, "achieved": flops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": flops / fp64_peak if fp64_peak else None,
+            "peak_source": "measured DFMA loop on all SMs (titgpu_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+            "alg_flops_per_particle": alg_flops_rhs(dim), "launches": cnt, "avg_ms": avg_s * 1e3,
             "share_of_step": tot / total_kernel_ms if total_kernel_ms else None,
-            "fp64": {"achieved_tflops": flops, "peak_tflops": fp64_peak, "frac": flops / fp64_peak if fp64_peak else None,
-                     "alg_flops_per_particle": alg_flops_rhs(dim), "peak_source": "measured DFMA loop (titgpu_measure_fp64_peak)"},
+            "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read + write)", "traffic_source": traffic_src,
+            "hbm": {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "alg_bytes_per_particle": alg_bytes_rhs(dim), "peak_source": peak_src,
+                    "dram_frac": (traffic / avg_s / 1e9 / hbm_peak) if traffic else None},
+            "pipes": ncu_pipes(dim),
             "step": {"alg_bytes_per_update": alg_bytes_step(dim), "achieved_gbs": alg_bytes_step(dim) * value / world / 1e9,
                      "frac": alg_bytes_step(dim) * value / world / 1e9 / hbm_peak},
         }
 
+    # ---- strong scaling beside the weak line (N > 1) ----------------------
+    strong = None
+    if world > 1 and not strong_main and not args.no_strong:
+        run.close()
+        del run, solver
+        sw = WORKLOADS[args.strong_workload]
+        srun = Runner(args, 3, args.strong_n_col or sw["n_col"], rank, local_rank, world, "strong_x")
+        s_steps = max(2, min(args.steps, 5))
+        s_ms, _, _, _ = srun.timed_steps(s_steps, 3, profile=False)
+        s_value = srun.n_total * s_steps / (s_ms * 1e-3)
+        ref = strong_reference()
+        same = bool(ref) and ref.get("n_total") == srun.n_total
+        strong = {"workload": sw["label"] if not args.strong_n_col else f"3D dam break, n_col={args.strong_n_col}", "n_total": srun.n_total, "value": s_value, "unit": UNIT, "steps": s_steps, "ms_per_step": s_ms / s_steps,
+                  "decomposition": f"{world} slabs of equally many lattice planes along x (fixed tank), halo 2R + dr_wall + dr",
+                  "one_gpu_value": ref["value"] if same else None, "one_gpu_source": "profiles/strong_c5_1gpu.json" if same else None,
+                  "efficiency": (s_value / (world * ref["value"])) if same else None}
+        srun.close()
+
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
         cpu, _, _, _ = cpu_baseline_sample(dim, args.cpu_budget)
+    if world == 1:
+        par = "single GPU"
+    elif strong_main:
+        par = f"{world} slabs along x of the fixed tank (strong scaling), one rank per GPU"
+    else:
+        par = f"{world} slabs along z (tank {world}x deeper: weak scaling), one rank per GPU"
+    if world > 1:
+        par += "; inside every step: migration + halo set, 4 ghost refreshes, {N, phi} and shifted-record exchanges (ncclSend/ncclRecv on the context's stream), dt all-reduce"
+    label = w["label"] if not args.n_col else f"{dim}D dam break, n_col={n_col}"
+    if world > 1 and not strong_main:
+        label += f", per GPU; {world} GPUs weak-scaled along z"
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (w["label"] if not args.n_col else f"{dim}D dam break, n_col={n_col}") + ("" if world == 1 else f", per GPU; {world} GPUs weak-scaled along z"), "particles_per_gpu": int(n), "n_fluid": case.n_fluid if slab is None else case.meta["n_fluid_global"], "n_fixed": case.n_fixed if slab is None else case.meta["n_fixed_global"],
-                   "integrator": "ssprk3", "kernel": "SixthOrderWendland", "eos": "tait", "parallelism": "single GPU" if world == 1 else f"{world} slabs along z (tank {world}x deeper), one rank per GPU, ghost-layer exchange over NCCL send/recv before every neighbour search, dt all-reduce per step",
+        "higher_is_better": True, "scaling": "strong" if strong_main else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": label, "particles_per_gpu": int(n), "n_fluid": int(n_fluid), "n_fixed": int(n_fixed),
+                   "integrator": "ssprk3", "kernel": "SixthOrderWendland", "eos": "tait", "parallelism": par,
                    "outputs": "value: all 17 fields of all particles published after the last timed step (reference semantics); e2e: state only (r, v, rho) every step",
                    "l2_policy": "inputs larger than L2 (state arrays of %d MB)" % (int(n) * (2 * dim + 2) * 8 // 2**20)},
         "clocks": clocks,
@@ -395,6 +469,8 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in top[:12]},
     }
+    if strong is not None:
+        out["strong"] = strong
     emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -444,6 +520,11 @@ def main():
     ap.add_argument("--ref-n-col", type=int, default=0, help="sample resolution of the CPU reference arm")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = the workload per GPU (tank N x deeper along z); strong = the workload itself cut into N slabs along x")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1, weak: skip the extra strong-scaling measurement (`strong` object)")
+    ap.add_argument("--strong-workload", default="c5", choices=["c3", "c4", "c5"])
+    ap.add_argument("--strong-n-col", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -123,42 +123,61 @@ TITGPU_API int titgpu_neighbors(titgpu_ctx* ctx, uint64_t* row_offsets, uint64_t
 
 /* ---- Slab domain decomposition (one context per GPU / rank) -------------------
  * Replaces, across GPUs, what the reference's block partition does across
- * threads (sph/particle_mesh.hpp:165-241; geom/partition/): every rank owns
- * the fluid particles of one slab plus GHOST copies of the neighbouring slabs'
- * particles within a halo, refreshed before every neighbour search. Ghosts are
- * neighbours only: their right-hand sides are not evaluated, their records
- * are replaced by the next exchange. The rank-local wall particles / faces are
- * those of the slab plus halo and never move. The host side (which particles
- * to send where, NCCL send/recv) lives above this ABI: titsolver_b200/slab.py.
+ * threads (sph/particle_mesh.hpp:165-241; geom/partition/sort_partition.hpp:25-75):
+ * every rank owns the fluid particles of one slab [lo, hi) along `axis` plus GHOST
+ * copies of the neighbouring slabs' particles within `halo` of its slab. Ghosts are
+ * neighbours only: their right-hand sides are not evaluated. The rank-local wall
+ * particles / faces are those of the slab plus halo and never move.
  *
- * Fluid records cross this part of the ABI as DEVICE arrays of 4 doubles per
- * particle in rank-local order (owned particles first, then ghosts):
+ * Everything a step needs from the other ranks happens INSIDE titgpu_step, on the
+ * context's stream (csrc/mg.cuh): migration of the particles that left the slab and
+ * selection of the halo set at the first neighbour search of a step, a fixed-size
+ * refresh of that set before each later search, {N, phi} and the shifted records inside
+ * the shifting pass (fluid_equations.hpp:409-414, 443-450, 489-511), and a MIN / MAX
+ * all-reduce of the time-step scalars (:203-221): ncclSend / ncclRecv / ncclAllReduce
+ * between the GPUs of a box. A host in any language sets the slab, attaches a
+ * communicator and calls titgpu_step; it never touches a ghost.
+ *
+ * Owned fluid records cross this part of the ABI as HOST arrays of 4 doubles per
+ * particle in rank-local order:
  *   3-D: A = {x, y, z, rho}  B = {vx, vy, vz, m}
  *   2-D: A = {x, y, rho, m}  B = {vx, vy, 0, 0}
- * A0 / B0 = the same at the beginning of the step (SSPRK u_old); may be NULL. */
+ * After the first step of a decomposed run the generic titgpu_upload / titgpu_download
+ * address rank-local ids (owned, then ghosts, then walls), whose number changes from
+ * step to step: use the _owned calls below instead. */
 
 /* Capacity for the fluid particles of this rank (owned + ghosts); call before
  * the first titgpu_upload. */
 TITGPU_API int titgpu_mg_reserve(titgpu_ctx* ctx, size_t max_fluid);
+/* The slab of this rank: owned particles have lo <= r[axis] < hi (use -HUGE_VAL / HUGE_VAL
+ * at the ends); `halo` = ghost-layer width including the margin for the motion within one
+ * step (2 support radii + the longest wall-face edge + one particle spacing covers every
+ * pass of the step). `fluid_total` >= 0 makes every step verify that the ranks together
+ * still own that many fluid particles. An interior slab thinner than `halo` is refused. */
+TITGPU_API int titgpu_mg_set_slab(titgpu_ctx* ctx, int axis, double lo, double hi, double halo, long long fluid_total);
+/* Global ids of the fluid particles uploaded so far (they travel with the particles). */
+TITGPU_API int titgpu_mg_set_gids(titgpu_ctx* ctx, const int64_t* gids);
+/* Communicator. Either adopt the host's ncclComm_t (rank r talks to r - 1 and r + 1), or
+ * let the library create one from an ncclUniqueId (128 bytes) made on one rank by
+ * titgpu_mg_nccl_unique_id and distributed by the host (MPI, torch.distributed, a file). */
+TITGPU_API int titgpu_mg_attach_comm(titgpu_ctx* ctx, void* nccl_comm, int rank, int nranks);
+TITGPU_API int titgpu_mg_nccl_unique_id(void* id128);
+TITGPU_API int titgpu_mg_attach_nccl(titgpu_ctx* ctx, const void* id128, int rank, int nranks);
+/* Ranks living in ONE process (one host thread per context, e.g. several ranks sharing a
+ * GPU in tests): device-to-device copies ordered by CUDA events instead of NCCL, the same
+ * exchange kernels. All ranks must call titgpu_step concurrently. */
+TITGPU_API void* titgpu_mg_hub_create(int nranks);
+TITGPU_API void titgpu_mg_hub_destroy(void* hub);
+TITGPU_API int titgpu_mg_attach_hub(titgpu_ctx* ctx, void* hub, int rank);
+TITGPU_API int titgpu_mg_detach(titgpu_ctx* ctx);
 /* Current numbers of owned, ghost and wall particles. */
 TITGPU_API int titgpu_mg_counts(titgpu_ctx* ctx, size_t* n_owned, size_t* n_ghost, size_t* n_fixed);
-/* Copy the fluid records (owned + ghosts, rank-local order) into caller buffers. */
-TITGPU_API int titgpu_mg_export(titgpu_ctx* ctx, double* A_dev, double* B_dev, double* A0_dev, double* B0_dev);
-/* Replace the fluid particles of the context by n_owned owned + n_ghost ghost
- * records (the wall particles stay). Asynchronous on the context's stream. */
-TITGPU_API int titgpu_mg_import(titgpu_ctx* ctx, size_t n_owned, size_t n_ghost, const double* A_dev, const double* B_dev, const double* A0_dev, const double* B0_dev);
-/* titgpu_step calls `fn(user, phase)` wherever the ranks must talk; a non-zero
- * return aborts the step. phase 0: before the first neighbour search of a step
- * (particles may change owner); 1: before the later searches of the right-hand
- * sides; 3: before the search of post_integrate (wider halo: the shifting /
- * free-surface passes read neighbours of neighbours); 2: reduce the time-step
- * scalars over the ranks — titgpu_mg_scalars()[2] with MIN, [1] with MAX
- * (both non-negative doubles; fluid_equations.hpp:203-221). The callback may
- * call titgpu_mg_export / titgpu_mg_import / titgpu_mg_counts on the context. */
-typedef int (*titgpu_exchange_fn)(void* user, int phase);
-TITGPU_API int titgpu_mg_set_exchange(titgpu_ctx* ctx, titgpu_exchange_fn fn, void* user);
-/* Device pointer to the step scalars {dt, max |dv_dt|^2, min dt candidate}. */
-TITGPU_API void* titgpu_mg_scalars(titgpu_ctx* ctx);
+/* The owned particles (global ids and records, rank-local order) to / from HOST buffers;
+ * any output pointer may be NULL. An upload drops the ghosts (the next step fetches them). */
+TITGPU_API int titgpu_mg_download_owned(titgpu_ctx* ctx, int64_t* gid, double* A, double* B, size_t cap, size_t* n_owned);
+TITGPU_API int titgpu_mg_upload_owned(titgpu_ctx* ctx, size_t n_owned, const int64_t* gid, const double* A, const double* B);
+/* Exchanges performed and particles migrated away so far. */
+TITGPU_API int titgpu_mg_stats(titgpu_ctx* ctx, unsigned long long* exchanges, unsigned long long* migrated);
 
 /* Block until all queued work of the context has finished. */
 TITGPU_API int titgpu_synchronize(titgpu_ctx* ctx);

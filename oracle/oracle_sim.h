@@ -51,7 +51,15 @@ struct SimBase {
   virtual void initialize() = 0;
   virtual void prepare() = 0;
   virtual void rhs_only() = 0;
+  virtual void post_only() = 0;
   virtual double step() = 0;
+  // Branch counters of the last post_integrate (tests assert that the interesting branches
+  // of fluid_equations.hpp:366-511 were exercised): [0] LU of L^T failed -> identity,
+  // [1] particles on the free surface after the visibility test + splash rule, [2] of those
+  // by the splash rule alone, [3] near-surface particles (phi scaled), [4] shifted particles,
+  // [5] shifted with the velocity correction skipped (|gamma - 1| > tiny), [6] free-surface
+  // corrections applied (ratio <= 0.99), [7] candidates of the correction (phi != 1).
+  long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   virtual void neighbors(std::vector<std::uint64_t>& off, std::vector<std::uint64_t>& cols) = 0;
   virtual void face_neighbors(std::vector<std::uint64_t>& off, std::vector<std::uint64_t>& cols) = 0;
 };
@@ -439,7 +447,12 @@ struct Sim final : SimBase {
       // :366-377
       dr[a] = Na;
       M Linv;
-      if (lu_inverse(transpose(La), Linv)) {
+      const bool lu_ok = lu_inverse(transpose(La), Linv);
+      if (!lu_ok) {
+#pragma omp atomic
+        stats[0]++;
+      }
+      if (lu_ok) {
         La = Linv;
         Na = matvec(La, Na);
         gv = matmul(gv, transpose(La));
@@ -474,7 +487,11 @@ struct Sim final : SimBase {
     // :419-426 splashes.
     const std::uint32_t cutoff = D == 2 ? 8 : 26;
     for (std::size_t a = 0; a < nf; ++a)
-      if (nb_off[a + 1] - nb_off[a] <= cutoff) phi[a] = phi_min;
+      if (nb_off[a + 1] - nb_off[a] <= cutoff) {
+        if (!bitwise_equal(phi[a], phi_min)) stats[2]++;
+        phi[a] = phi_min;
+      }
+    for (std::size_t a = 0; a < nf; ++a) stats[1] += bitwise_equal(phi[a], phi_min);
     // :440-452 near-surface scaling (two-phase: readers only compare with phi_min).
     std::vector<double> phi_new(phi);
 #pragma omp parallel for schedule(dynamic, 256)
@@ -492,6 +509,11 @@ struct Sim final : SimBase {
       if (found) phi_new[a] = phi[a] * (std::abs(dot(N[best], r[a] - r[best])) / rad);
     }
     phi.swap(phi_new);
+    for (std::size_t a = 0; a < nf; ++a) {
+      stats[3] += !bitwise_equal(phi[a], phi_max) && !bitwise_equal(phi[a], phi_min);
+      stats[4] += bitwise_equal(phi[a], phi_max);
+      stats[5] += bitwise_equal(phi[a], phi_max) && !approx_equal(gamma[a], 1.0);
+    }
     // :455-470
 #pragma omp parallel for schedule(static)
     for (std::size_t a = 0; a < nf; ++a) {
@@ -520,14 +542,20 @@ struct Sim final : SimBase {
         rho_t += m[b] * W;
       }
       const double ratio = std::min(1.0, alpha / gamma[a]);
+#pragma omp atomic
+      stats[7]++;
       if (ratio > 0.99) continue;
+#pragma omp atomic
+      stats[6]++;
       const double beta = std::exp(-K_fs * pow2(ratio - 1.0));
       const double corr = beta * gamma[a] + (1.0 - beta) * alpha;
       if (!is_tiny(corr)) rho[a] = rho_t / corr;
     }
   }
 
+  void post_only() override { post_integrate(); }
   void post_integrate() {
+    for (long long& x : stats) x = 0;
     prepare();
     apply_shifts();
     apply_free_surface_correction();

@@ -45,7 +45,8 @@ def load(fast: bool = False) -> C.CDLL:
     lib.orc_resize.argtypes = [vp, sz, sz]
     lib.orc_upload.argtypes = [vp, C.c_char_p, dp]
     lib.orc_download.argtypes = [vp, C.c_char_p, dp]
-    for f in ("orc_initialize", "orc_prepare", "orc_rhs_only"):
+    lib.orc_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
+    for f in ("orc_initialize", "orc_prepare", "orc_rhs_only", "orc_post_only"):
         getattr(lib, f).argtypes = [vp]
     lib.orc_step.argtypes = [vp, C.c_int, dp]
     lib.orc_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
@@ -150,6 +151,17 @@ class OracleSolver:
 
     def rhs_only(self):
         self.lib.orc_rhs_only(self.h)
+
+    def post_only(self):
+        self.lib.orc_post_only(self.h)
+
+    STAT_NAMES = ("lu_failed", "free_surface", "splash", "near_surface", "shifted", "shifted_no_v_correction", "fs_corrected", "fs_candidates")
+
+    def stats(self):
+        """Branch counters of the last post_integrate (oracle_sim.h, SimBase::stats)."""
+        a = (C.c_longlong * 8)()
+        self.lib.orc_stats(self.h, a)
+        return dict(zip(self.STAT_NAMES, [int(x) for x in a]))
 
     def step(self, nsteps=1):
         dt = C.c_double(0)

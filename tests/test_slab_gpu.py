@@ -1,8 +1,10 @@
 """Slab decomposition on the GPU: N ranks (one context each) must reproduce the
-single-context run of the same case. With fewer GPUs than ranks the ranks share
-a device and talk over gloo (payloads staged through the host); with enough
-GPUs they use NCCL. Results depend on the decomposition only through the order
-of the floating-point sums, hence the 1e-9 bound after a few steps."""
+single-context run of the same case. On a single-GPU box the ranks are threads of
+one process sharing the device (`--hub N`: event-ordered device copies instead of
+NCCL, the same exchange kernels - csrc/mg.cuh); with one GPU per rank
+tools/slab_check.py runs under torchrun over NCCL (profiles/). Results depend on
+the decomposition only through the order of the floating-point sums, hence the
+1e-9 bound after a few steps."""
 import json
 import os
 import subprocess
@@ -24,19 +26,31 @@ def run_check(*args):
 
 
 def test_two_slabs_2d():
-    # 80 particle layers along x: each slab (40) is wider than the widest halo (~18.4 dr)
-    res = run_check("--spawn", 2, "--dim", 2, "--n-col", 40, "--steps", 3)
+    # 80 particle layers along x: each slab (40) is wider than the halo (~10 dr)
+    res = run_check("--hub", 2, "--dim", 2, "--n-col", 40, "--steps", 3)
     assert all(c[1] > 0 for c in res["counts"])  # both ranks hold ghosts
+    assert all(e[0] >= 3 * 7 for e in res["exchanges_migrated"])  # 1 + 3 refreshes + N/phi + shifted per step (A and B count separately)
 
 
-def test_three_slabs_2d_with_migration():
-    """A random velocity kick makes particles change owner during the run."""
-    run_check("--spawn", 3, "--dim", 2, "--n-col", 30, "--steps", 4, "--kick", 3.0, "--tol", 1e-8)
+def test_four_slabs_2d_with_migration():
+    """A random velocity kick makes particles change owner during the run; interior
+    slabs have two neighbours."""
+    res = run_check("--hub", 4, "--dim", 2, "--n-col", 40, "--steps", 6, "--kick", 20.0, "--tol", 1e-7)
+    assert sum(e[1] for e in res["exchanges_migrated"]) > 0  # particles did migrate
 
 
 def test_two_slabs_3d():
-    run_check("--spawn", 2, "--dim", 3, "--n-col", 24, "--steps", 2)
+    run_check("--hub", 2, "--dim", 3, "--n-col", 24, "--steps", 2)
+
+
+def test_three_slabs_3d_benchmark_lattice():
+    run_check("--hub", 3, "--dim", 3, "--n-col", 20, "--steps", 2, "--lattice")
 
 
 def test_two_slabs_3d_along_z():
-    run_check("--spawn", 2, "--dim", 3, "--n-col", 10, "--steps", 2, "--axis", 2)
+    run_check("--hub", 2, "--dim", 3, "--n-col", 12, "--steps", 2, "--axis", 2)
+
+
+def test_two_slabs_2d_euler_and_verlet():
+    for integ in (0, 1):
+        run_check("--hub", 2, "--dim", 2, "--n-col", 30, "--steps", 3, "--integrator", integ)

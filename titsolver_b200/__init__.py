@@ -30,7 +30,9 @@ FIELDS = {
 ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
-    "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_mg_reserve", "titgpu_mg_counts", "titgpu_mg_export", "titgpu_mg_import", "titgpu_mg_set_exchange", "titgpu_mg_scalars",
+    "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_mg_reserve", "titgpu_mg_counts",
+    "titgpu_mg_set_slab", "titgpu_mg_set_gids", "titgpu_mg_attach_comm", "titgpu_mg_nccl_unique_id", "titgpu_mg_attach_nccl", "titgpu_mg_hub_create", "titgpu_mg_hub_destroy",
+    "titgpu_mg_attach_hub", "titgpu_mg_detach", "titgpu_mg_download_owned", "titgpu_mg_upload_owned", "titgpu_mg_stats",
     "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
     "titgpu_profile_enable", "titgpu_profile_reset", "titgpu_profile_count", "titgpu_profile_get", "titgpu_measure_fp64_peak",
 ]
@@ -41,9 +43,6 @@ class TitGpuError(RuntimeError):
 
 
 _lib = None
-
-
-EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
 
 
 def load_library() -> C.CDLL:
@@ -74,11 +73,20 @@ def load_library() -> C.CDLL:
     lib.titgpu_list_redos.restype = C.c_ulonglong
     lib.titgpu_mg_reserve.argtypes = [vp, sz]
     lib.titgpu_mg_counts.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
-    lib.titgpu_mg_export.argtypes = [vp, vp, vp, vp, vp]
-    lib.titgpu_mg_import.argtypes = [vp, sz, sz, vp, vp, vp, vp]
-    lib.titgpu_mg_set_exchange.argtypes = [vp, EXCHANGE_FN, vp]
-    lib.titgpu_mg_scalars.argtypes = [vp]
-    lib.titgpu_mg_scalars.restype = vp
+    lib.titgpu_mg_set_slab.argtypes = [vp, C.c_int, d, d, d, C.c_longlong]
+    lib.titgpu_mg_set_gids.argtypes = [vp, vp]
+    lib.titgpu_mg_attach_comm.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.titgpu_mg_nccl_unique_id.argtypes = [vp]
+    lib.titgpu_mg_attach_nccl.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.titgpu_mg_hub_create.argtypes = [C.c_int]
+    lib.titgpu_mg_hub_create.restype = vp
+    lib.titgpu_mg_hub_destroy.argtypes = [vp]
+    lib.titgpu_mg_hub_destroy.restype = None
+    lib.titgpu_mg_attach_hub.argtypes = [vp, vp, C.c_int]
+    lib.titgpu_mg_detach.argtypes = [vp]
+    lib.titgpu_mg_download_owned.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.titgpu_mg_upload_owned.argtypes = [vp, sz, vp, vp, vp]
+    lib.titgpu_mg_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.titgpu_launch_count.argtypes = [vp]
     lib.titgpu_launch_count.restype = C.c_ulonglong
     lib.titgpu_stream.argtypes = [vp]
@@ -91,6 +99,25 @@ def load_library() -> C.CDLL:
     lib.titgpu_measure_fp64_peak.argtypes = [vp, C.POINTER(d)]
     _lib = lib
     return lib
+
+
+def nccl_unique_id() -> bytes:
+    """An ncclUniqueId (128 bytes) for titgpu_mg_attach_nccl; make it on one rank, send it to the others."""
+    buf = C.create_string_buffer(128)
+    if load_library().titgpu_mg_nccl_unique_id(buf):
+        raise TitGpuError("titgpu_mg_nccl_unique_id failed (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
+def hub_create(nranks):
+    h = load_library().titgpu_mg_hub_create(int(nranks))
+    if not h:
+        raise TitGpuError("titgpu_mg_hub_create failed")
+    return h
+
+
+def hub_destroy(hub):
+    load_library().titgpu_mg_hub_destroy(hub)
 
 
 def _arr(x, dtype=np.float64):
@@ -204,21 +231,48 @@ class Solver:
         self._ck(self.lib.titgpu_mg_counts(self.h, C.byref(a), C.byref(b), C.byref(c)), "titgpu_mg_counts")
         return a.value, b.value, c.value
 
-    def mg_export(self, A_ptr, B_ptr, A0_ptr=None, B0_ptr=None):
-        self._ck(self.lib.titgpu_mg_export(self.h, A_ptr, B_ptr, A0_ptr, B0_ptr), "titgpu_mg_export")
+    def mg_set_slab(self, axis, lo, hi, halo, fluid_total=-1):
+        self._ck(self.lib.titgpu_mg_set_slab(self.h, int(axis), float(lo), float(hi), float(halo), int(fluid_total)), "titgpu_mg_set_slab")
 
-    def mg_import(self, n_owned, n_ghost, A_ptr, B_ptr, A0_ptr=None, B0_ptr=None):
-        self._ck(self.lib.titgpu_mg_import(self.h, int(n_owned), int(n_ghost), A_ptr, B_ptr, A0_ptr, B0_ptr), "titgpu_mg_import")
-        self.n_fluid = int(n_owned) + int(n_ghost)
+    def mg_set_gids(self, gids):
+        g = _arr(gids, np.int64)
+        assert len(g) == self.n_fluid
+        self._ck(self.lib.titgpu_mg_set_gids(self.h, g.ctypes.data), "titgpu_mg_set_gids")
 
-    def mg_set_exchange(self, fn):
-        """`fn(phase) -> int`; kept alive by the solver."""
-        self._exchange_cb = EXCHANGE_FN(lambda user, phase: int(fn(phase))) if fn is not None else EXCHANGE_FN(0)
-        self._ck(self.lib.titgpu_mg_set_exchange(self.h, self._exchange_cb, None), "titgpu_mg_set_exchange")
+    def mg_attach_nccl(self, id128: bytes, rank, nranks):
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._ck(self.lib.titgpu_mg_attach_nccl(self.h, buf, int(rank), int(nranks)), "titgpu_mg_attach_nccl")
 
-    @property
-    def mg_scalars(self):
-        return self.lib.titgpu_mg_scalars(self.h)
+    def mg_attach_comm(self, comm_ptr, rank, nranks):
+        self._ck(self.lib.titgpu_mg_attach_comm(self.h, comm_ptr, int(rank), int(nranks)), "titgpu_mg_attach_comm")
+
+    def mg_attach_hub(self, hub, rank):
+        self._ck(self.lib.titgpu_mg_attach_hub(self.h, hub, int(rank)), "titgpu_mg_attach_hub")
+
+    def mg_detach(self):
+        self._ck(self.lib.titgpu_mg_detach(self.h), "titgpu_mg_detach")
+
+    def mg_download_owned(self, A_ptr=None, B_ptr=None, gid_ptr=None, cap=None):
+        """Owned records into HOST buffers (raw addresses); returns n_owned. Without buffers: just the count."""
+        n = C.c_size_t(0)
+        self._ck(self.lib.titgpu_mg_download_owned(self.h, gid_ptr, A_ptr, B_ptr, int(cap if cap is not None else 0), C.byref(n)), "titgpu_mg_download_owned")
+        return int(n.value)
+
+    def mg_owned(self):
+        """(gid, A, B) of the owned particles as numpy arrays (rank-local order)."""
+        n = self.mg_counts()[0]
+        gid, A, B = np.empty(max(n, 1), np.int64), np.empty((max(n, 1), 4)), np.empty((max(n, 1), 4))
+        self.mg_download_owned(A.ctypes.data, B.ctypes.data, gid.ctypes.data, cap=max(n, 1))
+        return gid[:n], A[:n], B[:n]
+
+    def mg_upload_owned(self, n_owned, A_ptr, B_ptr, gid_ptr=None):
+        self._ck(self.lib.titgpu_mg_upload_owned(self.h, int(n_owned), gid_ptr, A_ptr, B_ptr), "titgpu_mg_upload_owned")
+        self.n_fluid = int(n_owned)
+
+    def mg_stats(self):
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self._ck(self.lib.titgpu_mg_stats(self.h, C.byref(a), C.byref(b)), "titgpu_mg_stats")
+        return int(a.value), int(b.value)
 
     def neighbors(self):
         nnz = C.c_size_t(0)

@@ -24,7 +24,7 @@ LIB = os.path.join(HERE, "libtitgpu" + ("_" + VARIANT if VARIANT else "") + ".so
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-ccbin", "/usr/bin/g++"]
-HEADERS = ["common.cuh", "context.h", "engine.cuh", "sph_kernel.cuh", "kernels_gen.cuh", "../../include/titgpu.h"]
+HEADERS = ["common.cuh", "context.h", "engine.cuh", "mg.cuh", "mg_transport.h", "sph_kernel.cuh", "kernels_gen.cuh", "../../include/titgpu.h"]
 
 
 def _newer(target, deps):
@@ -55,6 +55,11 @@ def build(dims=(2, 3), kernels=(0, 1, 2, 3, 4, 5), jobs=None, verbose=False, ptx
     if _newer(api_o, [api_src] + hdrs):
         tasks.append([NVCC, *ARCH, *FLAGS, "-c", api_src, "-o", api_o])
     objs = [api_o]
+    mgt_o = os.path.join(OBJ, "mg_transport.o")
+    mgt_src = os.path.join(CSRC, "mg_transport.cu")
+    if _newer(mgt_o, [mgt_src, os.path.join(CSRC, "mg_transport.h")]):
+        tasks.append([NVCC, *ARCH, *FLAGS, "-c", mgt_src, "-o", mgt_o])
+    objs.append(mgt_o)
     inst = os.path.join(CSRC, "inst.cu")
     extra = ["-Xptxas", "-v"] if ptxas_v else []
     for d in dims:
@@ -68,7 +73,7 @@ def build(dims=(2, 3), kernels=(0, 1, 2, 3, 4, 5), jobs=None, verbose=False, ptx
         with cf.ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 4)) as ex:
             outs = list(ex.map(_run, tasks))
     if tasks or _newer(LIB, objs):
-        _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ccbin", "/usr/bin/g++"])
+        _run([NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-ldl", "-ccbin", "/usr/bin/g++"])
     if verbose or ptxas_v:
         for o in outs:
             if o.strip():

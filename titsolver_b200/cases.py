@@ -296,16 +296,21 @@ def tetra_tank_3d(n_side: int = 10, L: float = 1.0, wall_ratio: float = 0.93, ji
                 meta={"name": f"tetra_tank_3d_{n_side}", "wall_ratio": wall_ratio, "jitter": jitter})
 
 
-def dam_break_3d_slab(n_col: int, world: int, rank: int, H: float = 0.6, tank=(5.366, 4.0, 1.0), halo_cells: int = 26):
-    """Rank-local part of the weak-scaling 3-D dam break: the tank of
-    `dam_break_3d` made `world` times deeper along z (the flow is z-invariant, so
-    the slabs stay balanced for the whole run), cut into `world` slabs along z.
+def dam_break_3d_slab(n_col: int, world: int, rank: int, H: float = 0.6, tank=(5.366, 4.0, 1.0), halo_cells: int = 18, mode: str = "weak_z"):
+    """Rank-local part of a decomposed 3-D dam break.
 
-    Returns (case, edges): `case` holds the fluid particles this rank owns
+    mode "weak_z"   (weak scaling) the tank of `dam_break_3d` made `world` times deeper
+                    along z (the flow is z-invariant, so the slabs stay balanced), cut into
+                    `world` slabs along z;
+    mode "strong_x" (strong scaling) the tank of `dam_break_3d` itself, the fluid column cut
+                    into `world` slabs of equally many lattice planes along x; the last
+                    rank also holds the dry part of the tank.
+
+    Returns (case, edges, axis): `case` holds the fluid particles this rank owns
     (`case.meta["gid"]` = their global lattice indices), the wall vertices /
     faces within `halo_cells` wall cells of the slab (fixed particles = those
     vertices) and the global containment box. Coordinates are bit-identical to
-    those of the global case `dam_break_3d(n_col, tank=(.., .., world * tank_z))`.
+    those of the global case (`dam_break_3d(n_col, tank=...)`).
     """
     dr = H / float(n_col)
     g, rho0 = 9.81, 1000.0
@@ -313,22 +318,33 @@ def dam_break_3d_slab(n_col: int, world: int, rank: int, H: float = 0.6, tank=(5
     h0 = 2.0 * dr
     m0 = rho0 * dr**3
     mu = 0.001
-    tz = tank[2] * world
+    if mode == "weak_z":
+        axis, tz = 2, tank[2] * world
+    elif mode == "strong_x":
+        axis, tz = 0, tank[2]
+    else:
+        raise ValueError(mode)
     ext = (tank[0] * H, tank[1] * H, tz * H)
     ncell = tuple(max(1, int(math.ceil(e / dr - 1e-9))) for e in ext)
     WM, WN, WK = 2 * n_col, n_col, int(round(tz * n_col)) - 1
-    per = int(round(tank[2] * n_col))  # lattice planes per slab
-    # slab edges half-way between lattice planes: plane index k (z = dr (k + 1)) belongs to rank (k + 1) // per
-    edges = [-math.inf] + [dr * (per * j - 0.5) for j in range(1, world)] + [math.inf]
-    k0 = max(per * rank - 1, 0) if rank > 0 else 0
-    k1 = per * (rank + 1) - 1 if rank < world - 1 else WK
-    ii, jj, kk = np.meshgrid(np.arange(WM), np.arange(WN), np.arange(k0, k1), indexing="ij")
+    dims = (WM, WN, WK)
+    if mode == "weak_z":
+        per = int(round(tank[2] * n_col))  # lattice planes per slab: plane k (z = dr (k + 1)) belongs to rank (k + 1) // per
+        cuts = [0] + [per * j - 1 for j in range(1, world)] + [WK]
+    else:
+        cuts = [(WM * j) // world for j in range(world + 1)]
+    # slab edges half-way between lattice planes (plane i sits at dr (i + 1))
+    edges = [-math.inf] + [dr * (cuts[j] + 0.5) for j in range(1, world)] + [math.inf]
+    k0, k1 = cuts[rank], cuts[rank + 1]
+    rng = [np.arange(d) for d in dims]
+    rng[axis] = np.arange(k0, k1)
+    ii, jj, kk = np.meshgrid(*rng, indexing="ij")
     ii, jj, kk = ii.ravel(), jj.ravel(), kk.ravel()
     rf = dr * np.stack([ii + 1.0, jj + 1.0, kk + 1.0], axis=1)
     gid = (ii.astype(np.int64) * WN + jj) * WK + kk
     c0 = (k0 + 1) - halo_cells if rank > 0 else 0
-    c1 = (k1 + 1) + halo_cells if rank < world - 1 else ncell[2]
-    verts, faces = _box_wall_mesh(ext, ncell, inward=True, cell_range=(2, c0, c1))
+    c1 = (k1 + 1) + halo_cells if rank < world - 1 else ncell[axis]
+    verts, faces = _box_wall_mesh(ext, ncell, inward=True, cell_range=(axis, c0, c1))
     cverts, cfaces = _box_wall_mesh(ext, (1, 1, 1), inward=False)
     mg = 0.5 * dr
     cverts = np.where(cverts > 0.0, cverts + mg, cverts - mg)
@@ -339,6 +355,6 @@ def dam_break_3d_slab(n_col: int, world: int, rank: int, H: float = 0.6, tank=(5
     rho[:nf] = rho0 + rho0 * g * (H - rf[:, 1]) / cs0**2
     n_fixed_global = int(np.prod([c + 1 for c in ncell]) - np.prod([c - 1 for c in ncell]))
     case = Case(3, nf, nx, r, m, rho, verts, faces, cverts, cfaces, g, mu, cs0, rho0, 7.0, h0, dr, H,
-                {"name": f"dam_break_3d_{WM}x{WN}x{WK}_slab{rank}of{world}", "tank": ext, "gid": gid,
+                {"name": f"dam_break_3d_{WM}x{WN}x{WK}_{mode}_slab{rank}of{world}", "tank": ext, "gid": gid,
                  "n_fluid_global": WM * WN * WK, "n_fixed_global": n_fixed_global})
-    return case, edges
+    return case, edges, axis

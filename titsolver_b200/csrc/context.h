@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -47,6 +48,28 @@ struct DBuf {
 };
 
 struct EngineVTable;
+struct MgTransport;
+
+// Slab decomposition across GPUs (mg.cuh): the rank's slab, its transport and the
+// buffers of the ghost-layer exchange.
+struct MgState {
+  MgTransport* tr = nullptr;  // owned; null = single context
+  int axis = 0;
+  double lo = -HUGE_VAL, hi = HUGE_VAL;  // owned slab [lo, hi) along `axis`
+  double halo = 0;                       // ghost-layer width (incl. the margin for the motion within a step)
+  int left = -1, right = -1;             // neighbour ranks (-1 = none)
+  // The halo set of the current step: n_send[s] owned particles go to side s (0 left, 1 right),
+  // n_recv[s] ghosts come from it. Buffers hold [left part | right part].
+  size_t n_send[2] = {0, 0}, n_recv[2] = {0, 0};
+  bool set_valid = false;
+  DBuf sendA, sendB, recvA, recvB, send_idx;
+  DBuf migA[2], migB[2], migG[2];  // records / global ids of the particles leaving to side s
+  DBuf gid, gid_alt;               // global id by local id (owned particles)
+  DBuf flags, scans, pos_of, cub_tmp, bad;
+  DBuf stageA, stageB;             // owned records in local-id order (titgpu_mg_download_owned / _upload_owned)
+  unsigned long long exchanges = 0, migrated = 0;
+  long long fluid_total = -1;  // global number of fluid particles (conservation check), -1 = unchecked
+};
 
 struct Ctx {
   int device = 0, dim = 2, kernel_id = 4, eos_id = 0, integrator_id = 3;
@@ -61,8 +84,7 @@ struct Ctx {
   // Slab decomposition (titgpu_mg_*): capacity reserved for a varying number of
   // fluid particles, and the callback the step invokes where ranks must talk.
   size_t reserve_fluid = 0, cap_n = 0;
-  int (*exchange_fn)(void*, int) = nullptr;
-  void* exchange_user = nullptr;
+  MgState mg;
   // Step-persistent candidate lists (engine.cuh, "candidate lists"): built once
   // per step with a skin, reused by every neighbour pass of the step.
   bool lists_enabled = false;  // titgpu_set_lists / TITGPU_LISTS=1 (measured: no gain on B200)
@@ -175,8 +197,9 @@ struct EngineVTable {
   int (*neighbors)(Ctx&, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz);
   int (*download_state)(Ctx&, int field, double* dst_dev);  // unsort into original order
   int (*upload_state)(Ctx&, int field, const double* src_dev);
-  int (*mg_export)(Ctx&, double* A_dev, double* B_dev, double* A0_dev, double* B0_dev);
-  int (*mg_import)(Ctx&, size_t n_owned, size_t n_ghost, const double* A_dev, const double* B_dev, const double* A0_dev, const double* B0_dev);
+  // Slab decomposition: owned records in local-id order to / from device staging buffers.
+  int (*mg_gather_owned)(Ctx&, double* A_dev, double* B_dev);
+  int (*mg_replace_owned)(Ctx&, size_t n_owned, const double* A_dev, const double* B_dev);
 };
 
 const EngineVTable* get_engine(int dim, int kernel_id);

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "context.h"
+#include "mg_transport.h"
 
 struct titgpu_ctx {
   titgpu::Ctx c;
@@ -141,6 +142,11 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
   for (auto& p : c.prof_pending) { cudaEventDestroy(p.beg); cudaEventDestroy(p.end); }
   for (DBuf& b : c.out) b.release();
+  delete c.mg.tr;
+  c.mg.tr = nullptr;
+  for (DBuf* b : {&c.mg.sendA, &c.mg.sendB, &c.mg.recvA, &c.mg.recvB, &c.mg.send_idx, &c.mg.migA[0], &c.mg.migA[1], &c.mg.migB[0], &c.mg.migB[1], &c.mg.migG[0], &c.mg.migG[1], &c.mg.gid,
+                  &c.mg.gid_alt, &c.mg.flags, &c.mg.scans, &c.mg.pos_of, &c.mg.cub_tmp, &c.mg.bad, &c.mg.stageA, &c.mg.stageB})
+    b->release();
   if (c.stream) cudaStreamDestroy(c.stream);
   delete h;
   return 0;
@@ -318,12 +324,6 @@ int titgpu_mg_reserve(titgpu_ctx* h, size_t max_fluid) {
   c.reserve_fluid = max_fluid;
   return 0;
 }
-int titgpu_mg_set_exchange(titgpu_ctx* h, titgpu_exchange_fn fn, void* user) {
-  if (!h) return 1;
-  h->c.exchange_fn = fn;
-  h->c.exchange_user = user;
-  return 0;
-}
 int titgpu_mg_counts(titgpu_ctx* h, size_t* n_owned, size_t* n_ghost, size_t* n_fixed) {
   if (!h) return 1;
   Ctx& c = h->c;
@@ -332,22 +332,118 @@ int titgpu_mg_counts(titgpu_ctx* h, size_t* n_owned, size_t* n_ghost, size_t* n_
   if (n_fixed) *n_fixed = c.nx;
   return 0;
 }
-int titgpu_mg_export(titgpu_ctx* h, double* A_dev, double* B_dev, double* A0_dev, double* B0_dev) {
-  TITGPU_ENTER(true)
-  if (!A_dev || !B_dev || (!A0_dev) != (!B0_dev)) return fail(c, "titgpu_mg_export: bad buffers");
-  if (c.vt->mg_export(c, A_dev, B_dev, A0_dev, B0_dev)) return 1;
-  TIT_CUDA_OK(c, cudaGetLastError());
+int titgpu_mg_set_slab(titgpu_ctx* h, int axis, double lo, double hi, double halo, long long fluid_total) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (axis < 0 || axis >= c.dim) return fail(c, "titgpu_mg_set_slab: bad axis");
+  if (!(lo < hi)) return fail(c, "titgpu_mg_set_slab: empty slab");
+  if (!(halo > 0)) return fail(c, "titgpu_mg_set_slab: the halo width must be positive");
+  // Ghosts come from the adjacent slabs only: an interior slab thinner than the halo would
+  // need particles of the slab after next (and could lose particles that cross it in one step).
+  if (std::isfinite(lo) && std::isfinite(hi) && hi - lo < halo) return fail(c, "titgpu_mg_set_slab: interior slab thinner than the halo (use fewer ranks)");
+  c.mg.axis = axis; c.mg.lo = lo; c.mg.hi = hi; c.mg.halo = halo; c.mg.fluid_total = fluid_total;
+  c.mg.set_valid = false;
   return 0;
 }
-int titgpu_mg_import(titgpu_ctx* h, size_t n_owned, size_t n_ghost, const double* A_dev, const double* B_dev, const double* A0_dev, const double* B0_dev) {
+int titgpu_mg_set_gids(titgpu_ctx* h, const int64_t* gids) {
   TITGPU_ENTER(true)
-  if ((n_owned + n_ghost) && (!A_dev || !B_dev)) return fail(c, "titgpu_mg_import: bad buffers");
-  if ((!A0_dev) != (!B0_dev)) return fail(c, "titgpu_mg_import: bad buffers");
-  if (c.vt->mg_import(c, n_owned, n_ghost, A_dev, B_dev, A0_dev, B0_dev)) return 1;
-  TIT_CUDA_OK(c, cudaGetLastError());
+  if (!gids) return fail(c, "titgpu_mg_set_gids: null");
+  TIT_CUDA_OK(c, c.mg.gid.ensure(c.cap_n * 8));
+  if (c.nf) TIT_CUDA_OK(c, cudaMemcpyAsync(c.mg.gid.p, gids, c.nf * 8, cudaMemcpyHostToDevice, c.stream));
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
   return 0;
 }
-void* titgpu_mg_scalars(titgpu_ctx* h) { return h ? h->c.scalars.p : nullptr; }
+namespace {
+int mg_attach(Ctx& c, MgTransport* t, const std::string& err) {
+  if (!t) return fail(c, err);
+  delete c.mg.tr;
+  c.mg.tr = t;
+  c.mg.left = t->rank() > 0 ? t->rank() - 1 : -1;
+  c.mg.right = t->rank() + 1 < t->nranks() ? t->rank() + 1 : -1;
+  c.mg.set_valid = false;
+  return 0;
+}
+}  // namespace
+int titgpu_mg_nccl_unique_id(void* id128) {
+  std::string err;
+  return id128 ? nccl_unique_id(id128, err) : 1;
+}
+int titgpu_mg_attach_nccl(titgpu_ctx* h, const void* id128, int rank, int nranks) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (!id128 || rank < 0 || rank >= nranks) return fail(c, "titgpu_mg_attach_nccl: bad arguments");
+  std::string err;
+  return mg_attach(c, make_nccl_transport(id128, rank, nranks, c.device, err), err);
+}
+int titgpu_mg_attach_comm(titgpu_ctx* h, void* nccl_comm, int rank, int nranks) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (rank < 0 || rank >= nranks) return fail(c, "titgpu_mg_attach_comm: bad arguments");
+  std::string err;
+  return mg_attach(c, adopt_nccl_comm(nccl_comm, rank, nranks, err), err);
+}
+void* titgpu_mg_hub_create(int nranks) { return make_hub(nranks); }
+void titgpu_mg_hub_destroy(void* hub) { destroy_hub(static_cast<MgHub*>(hub)); }
+int titgpu_mg_attach_hub(titgpu_ctx* h, void* hub, int rank) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  TIT_CUDA_OK(c, cudaSetDevice(c.device));
+  std::string err;
+  return mg_attach(c, make_hub_transport(static_cast<MgHub*>(hub), rank, err), err);
+}
+int titgpu_mg_detach(titgpu_ctx* h) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (c.stream) { cudaSetDevice(c.device); cudaStreamSynchronize(c.stream); }
+  delete c.mg.tr;
+  c.mg.tr = nullptr;
+  c.mg.left = c.mg.right = -1;
+  return 0;
+}
+int titgpu_mg_download_owned(titgpu_ctx* h, int64_t* gid, double* A, double* B, size_t cap, size_t* n_owned) {
+  TITGPU_ENTER(true)
+  const size_t no = size_t(c.prm.n_owned);
+  if (n_owned) *n_owned = no;
+  if (!A && !B && !gid) return 0;
+  if (cap < no) return fail(c, "titgpu_mg_download_owned: capacity too small");
+  TIT_CUDA_OK(c, c.mg.stageA.ensure(std::max<size_t>(c.cap_n, 1) * sizeof(double4)));
+  TIT_CUDA_OK(c, c.mg.stageB.ensure(std::max<size_t>(c.cap_n, 1) * sizeof(double4)));
+  if (c.vt->mg_gather_owned(c, c.mg.stageA.as<double>(), c.mg.stageB.as<double>())) return 1;
+  if (no) {
+    if (A) TIT_CUDA_OK(c, cudaMemcpyAsync(A, c.mg.stageA.p, no * sizeof(double4), cudaMemcpyDeviceToHost, c.stream));
+    if (B) TIT_CUDA_OK(c, cudaMemcpyAsync(B, c.mg.stageB.p, no * sizeof(double4), cudaMemcpyDeviceToHost, c.stream));
+    if (gid) {
+      if (c.mg.gid.bytes >= no * 8) TIT_CUDA_OK(c, cudaMemcpyAsync(gid, c.mg.gid.p, no * 8, cudaMemcpyDeviceToHost, c.stream));
+      else for (size_t i = 0; i < no; ++i) gid[i] = int64_t(i);
+    }
+  }
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  TITGPU_LEAVE()
+}
+int titgpu_mg_upload_owned(titgpu_ctx* h, size_t n_owned, const int64_t* gid, const double* A, const double* B) {
+  TITGPU_ENTER(true)
+  if (n_owned && (!A || !B)) return fail(c, "titgpu_mg_upload_owned: null records");
+  if (n_owned + c.nx > c.cap_n) return fail(c, "titgpu_mg_upload_owned: more particles than reserved (titgpu_mg_reserve)");
+  TIT_CUDA_OK(c, c.mg.stageA.ensure(std::max<size_t>(c.cap_n, 1) * sizeof(double4)));
+  TIT_CUDA_OK(c, c.mg.stageB.ensure(std::max<size_t>(c.cap_n, 1) * sizeof(double4)));
+  if (n_owned) {
+    TIT_CUDA_OK(c, cudaMemcpyAsync(c.mg.stageA.p, A, n_owned * sizeof(double4), cudaMemcpyHostToDevice, c.stream));
+    TIT_CUDA_OK(c, cudaMemcpyAsync(c.mg.stageB.p, B, n_owned * sizeof(double4), cudaMemcpyHostToDevice, c.stream));
+    if (gid) {
+      TIT_CUDA_OK(c, c.mg.gid.ensure(c.cap_n * 8));
+      TIT_CUDA_OK(c, cudaMemcpyAsync(c.mg.gid.p, gid, n_owned * 8, cudaMemcpyHostToDevice, c.stream));
+    }
+  }
+  if (c.vt->mg_replace_owned(c, n_owned, c.mg.stageA.as<double>(), c.mg.stageB.as<double>())) return 1;
+  TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
+  TITGPU_LEAVE()
+}
+int titgpu_mg_stats(titgpu_ctx* h, unsigned long long* exchanges, unsigned long long* migrated) {
+  if (!h) return 1;
+  if (exchanges) *exchanges = h->c.mg.exchanges;
+  if (migrated) *migrated = h->c.mg.migrated;
+  return 0;
+}
 
 int titgpu_neighbors(titgpu_ctx* h, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz) {
   TITGPU_ENTER(true)

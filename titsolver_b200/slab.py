@@ -1,11 +1,18 @@
 """Slab domain decomposition of the WCSPH step across the GPUs of one box.
 
 One process per GPU. Every rank owns the fluid particles of one slab
-[lo, hi) along `axis` and, before every neighbour search, receives GHOST copies
-of the neighbouring slabs' particles within a halo (NCCL send/recv over NVLink
-through torch.distributed; gloo on CPU for the tests). Ghosts are neighbours
-only. Ownership changes once per step, at its first search. The time-step
-scalars are reduced over the ranks once per step (MIN / MAX all-reduce).
+[lo, hi) along `axis` and keeps GHOST copies of the neighbouring slabs'
+particles within a halo. The exchanges themselves (migration, halo set, the
+refreshes before every neighbour search, {N, phi} and the shifted records
+inside the shifting pass, the dt all-reduce) run INSIDE `titgpu_step` on the
+context's stream: packing kernels + ncclSend / ncclRecv (csrc/mg.cuh,
+csrc/mg_transport.cu). This module only cuts the case into slabs, hands every
+rank's context its slab, halo width and communicator, and gathers results.
+
+`exchange_records` / `NeighbourComm` below are the executable SPECIFICATION of
+what one device-side exchange must deliver (owned + ghosts reproduce the global
+neighbour sets; migration is a partition): pure torch, driven over gloo on CPU
+by tests/test_slab_gloo.py.
 
 This is the multi-GPU replacement of the reference's block partition
 (/root/reference/source/tit/sph/particle_mesh.hpp:165-241), which splits the
@@ -13,15 +20,12 @@ particles among CPU threads with geom/partition/* and orders the pair loops so
 that threads never touch the same particle; here slabs never touch the same
 particle because every rank only updates what it owns.
 
-Halo widths (R = support radius, dw = largest wall-face edge):
-  right-hand-side searches  W = 2 R + dw   (a neighbour's wall density needs the
-                                            fluid within R of a wall vertex that
-                                            is within R + dw of an owned particle)
-  post_integrate search     W = 4 R + dw   (free-surface correction reads shifted
-                                            neighbours, whose shift reads N / phi
-                                            of their neighbours, whose sums read
-                                            wall densities: fluid_equations.hpp:331-512)
-plus a margin for the motion within a step.
+Halo width (R = support radius, dw = largest wall-face edge): W = 2 R + dw plus a
+margin for the motion within a step - an owned particle's wall terms read the
+density of wall particles within R + dw, which is extrapolated from the fluid
+within R of them (fluid_equations.hpp:122-164). Everything farther away that
+the shifting / free-surface passes read of a neighbour (N, phi, the shifted
+state: fluid_equations.hpp:409-414, 443-450, 489-511) is sent by its owner.
 
 `exchange_records` and `SlabLayout` are pure torch and device-agnostic: the
 CPU tests drive exactly this code over gloo.
@@ -178,55 +182,66 @@ def local_surface(verts: np.ndarray, faces: np.ndarray, axis: int, lo: float, hi
     return verts[vid], inv.reshape(f.shape).astype(np.uint64), vid
 
 
-class _DevicePtr:
-    """A raw CUDA pointer as a torch-importable array (`__cuda_array_interface__`)."""
-
-    def __init__(self, ptr, n, typestr="<f8"):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+def halo_width(case, kernel_id=4, margin_dr=1.0):
+    """(halo, R, dw): ghost-layer width 2 R + dw + margin, support radius, longest wall-face edge."""
+    R = 2.0 * case.h if kernel_id not in (1, 2) else (2.5 if kernel_id == 1 else 3.0) * case.h
+    dw = 0.0
+    if len(case.faces):
+        f = case.faces[: min(len(case.faces), 200000)].astype(np.int64)
+        v = case.verts[f]
+        for i in range(case.dim):
+            d = v[:, i] - v[:, (i + 1) % case.dim]
+            dw = max(dw, float(np.sqrt((d * d).sum(axis=1)).max()))
+    return 2.0 * R + dw + margin_dr * case.dr, R, dw
 
 
 class SlabSolver:
-    """`titsolver_b200.Solver` of one rank + the halo exchange around it."""
+    """`titsolver_b200.Solver` of one rank, configured as one slab of a decomposed run.
+
+    transport: `hub=<titsolver_b200.hub_create(world)>` for ranks that share a process
+    (one thread each); otherwise NCCL - the ncclUniqueId made on rank 0 travels through
+    torch.distributed (any backend), the communicator itself belongs to libtitgpu."""
 
     MARGIN_DR = 1.0  # extra halo, in particle spacings, for the motion within one step
 
-    def __init__(self, case, rank, world, axis=0, edges=None, device=0, kernel_id=4, eos_id=0, integrator_id=3, group=None, reserve=None, local=False):
+    def __init__(self, case, rank, world, axis=0, edges=None, device=0, kernel_id=4, eos_id=0, integrator_id=3, group=None, reserve=None, local=False, hub=None,
+                 fluid_total=None):
         """`case` is the GLOBAL case (every rank cuts out its slab; small runs and
         tests) or, with `local=True`, the rank-local one made by
         `cases.dam_break_3d_slab` (`edges` required, `case.meta["gid"]` = global ids)."""
         import titsolver_b200 as tb
 
         self.rank, self.world, self.axis = rank, world, axis
-        self.comm = NeighbourComm(rank, world, group)
         self.dim = case.dim
         nf = case.n_fluid
-        R = 2.0 * case.h if kernel_id not in (1, 2) else (2.5 if kernel_id == 1 else 3.0) * case.h
-        dw = self._max_face_edge(case)
-        m = self.MARGIN_DR * case.dr
+        halo, R, dw = halo_width(case, kernel_id, self.MARGIN_DR)
         if not local:
             edges = edges or balanced_edges(case.r[:nf, axis], world)
-        self.layout = SlabLayout(axis, edges, 2 * R + dw + m, 4 * R + dw + m)
+            fluid_total = nf if fluid_total is None else fluid_total
+        elif fluid_total is None:
+            fluid_total = case.meta.get("n_fluid_global", -1)
+        self.layout = SlabLayout(axis, edges, halo, halo)
         lo, hi = self.layout.bounds(rank)
         self.lo, self.hi = lo, hi
         if not local:
             x = case.r[:nf, axis]
             own = np.nonzero((x >= lo) & (x < hi))[0]
-            wf = self.layout.w_post + R + 2 * dw
+            wf = halo + R + 2 * dw
             lverts, lfaces, vid = local_surface(case.verts, case.faces, axis, lo - wf, hi + wf)
             r = np.concatenate([case.r[own], lverts], axis=0)
             mass = np.concatenate([case.m[own], case.m[nf + vid]])
             rho = np.concatenate([case.rho[own], case.rho[nf + vid]])
             gid = own.astype(np.int64)
-            if reserve is None:  # owned + the particles now inside the widest halo, with head-room
-                w = self.layout.w_post
-                reserve = int(1.3 * np.count_nonzero((x >= lo - w) & (x < hi + w))) + 4096
+            if reserve is None:  # owned + the particles now inside the halo, with head-room
+                reserve = int(1.3 * np.count_nonzero((x >= lo - halo) & (x < hi + halo))) + 4096
         else:
             lverts, lfaces, r, mass, rho, gid = case.verts, case.faces, case.r, case.m, case.rho, np.asarray(case.meta["gid"], dtype=np.int64)
             if reserve is None:  # both halos at the slab's particle density
                 x = case.r[:nf, axis]
-                width = max(float(x.max() - x.min()) + case.dr, case.dr)
-                reserve = int(1.3 * nf * (1.0 + 2.0 * self.layout.w_post / width)) + 4096
+                width = max(float(x.max() - x.min()) + case.dr, case.dr) if nf else case.dr
+                reserve = int(1.25 * nf * (1.0 + 2.0 * halo / width)) + 4096
         self.n_fixed = len(lverts)
+        self.gid0 = gid  # global ids of the initially owned particles, in upload order
         self.solver = s = tb.Solver(case.dim, kernel_id, eos_id, integrator_id, device=device)
         s.set_params(case.g, case.mu, case.cs0, case.rho0, case.xi, case.h)
         s.set_surface(lverts, lfaces, case.cverts, case.cfaces)
@@ -236,134 +251,38 @@ class SlabSolver:
         s.upload("r", r)
         s.upload("m", mass)
         s.upload("rho", rho)
-        self.torch_device = torch.device("cuda", device)
-        self.gid = torch.from_numpy(gid).to(self.torch_device)
-        self._stream = torch.cuda.ExternalStream(s.stream, device=self.torch_device)
-        self._exc = None
-        self._bufs, self._buf_cap = [], 0
-        self.fast_ghost_refresh = True
-        self.exchange_ms = 0.0
-        s.mg_set_exchange(self._on_exchange)
+        s.mg_set_gids(gid)
+        s.mg_set_slab(axis, lo, hi, halo, fluid_total)
+        if world > 1:
+            if hub is not None:
+                s.mg_attach_hub(hub, rank)
+            else:
+                box = [tb.nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0, group=group)
+                s.mg_attach_nccl(box[0], rank, world)
 
-    @staticmethod
-    def _max_face_edge(case):
-        if len(case.faces) == 0:
-            return 0.0
-        f = case.faces[: min(len(case.faces), 200000)].astype(np.int64)
-        v = case.verts[f]
-        e = 0.0
-        for i in range(case.dim):
-            d = v[:, i] - v[:, (i + 1) % case.dim]
-            e = max(e, float(np.sqrt((d * d).sum(axis=1)).max()))
-        return e
-
-    # ---- the exchange callback (invoked from inside titgpu_step) ----
-    def _on_exchange(self, phase):
-        try:
-            with torch.cuda.stream(self._stream):
-                if phase == 2:
-                    sc = torch.as_tensor(_DevicePtr(self.solver.mg_scalars, 3), device=self.torch_device)
-                    self.comm.allreduce_min_max(sc[2:3], sc[1:2])
-                else:
-                    self._halo(migrate=(phase == 0), halo=self.layout.w_post if phase == 3 else self.layout.w_rhs, with_old=(phase != 0 and self.solver_integrator_has_old))
-            return 0
-        except Exception as e:  # surfaces through titgpu_step's status
-            self._exc = e
-            return 1
-
-    @property
-    def solver_integrator_has_old(self):
-        return True
-
-    def _export(self, with_old):
-        n_owned, n_ghost, _ = self.solver.mg_counts()
-        nf = n_owned + n_ghost
-        bufs = [torch.empty((max(nf, 1), 4), dtype=torch.float64, device=self.torch_device) for _ in range(4 if with_old else 2)]
-        ptrs = [b.data_ptr() for b in bufs] + [None] * (4 - len(bufs))
-        self.solver.mg_export(*ptrs)
-        return torch.cat([b[:nf] for b in bufs], dim=1), n_owned
-
-    def _halo_ghosts(self, halo, with_old):
-        """Refresh of the ghost layer without a change of ownership (every exchange of a
-        step but the first): the owned records never leave the export buffers. They are
-        exported once, the rows within `halo` of a slab edge are sent, the received
-        ghosts are written behind the owned rows of the same buffers and those are
-        imported back - two passes over the rank's records instead of the six of the
-        general path (concatenations, boolean gathers)."""
+    def upload_owned_field(self, field, values):
+        """Set `field` ("v", "rho", ...) of the owned particles before the first step
+        (`values` in this rank's owned order; wall particles keep zeros / their values)."""
         s = self.solver
-        n_owned, n_ghost, _ = s.mg_counts()
-        nf = n_owned + n_ghost
-        k = 4 if with_old else 2
-        cap = max(self._buf_cap, nf)
-        if len(self._bufs) < k or self._bufs[0].shape[0] < cap:
-            cap = int(cap * 1.1) + 1024
-            self._bufs = [torch.empty((cap, 4), dtype=torch.float64, device=self.torch_device) for _ in range(4)]
-            self._buf_cap = cap
-        bufs = self._bufs[:k]
-        s.mg_export(*([b.data_ptr() for b in bufs] + [None] * (4 - k)))
-        A, B = bufs[0], bufs[1]
-        x = A[:n_owned, self.axis]
-        gown = self.gid[:n_owned]
-        comm = self.comm
-
-        def payload(mask):
-            idx = torch.nonzero(mask).squeeze(1)
-            return torch.cat([A[idx], B[idx], gown[idx].to(torch.float64).unsqueeze(1)], dim=1)
-
-        empty = torch.empty((0, 9), dtype=torch.float64, device=self.torch_device)
-        to_l = payload(x < self.lo + halo) if comm.left is not None else empty
-        to_r = payload(x >= self.hi - halo) if comm.right is not None else empty
-        from_l, from_r = comm.sendrecv(to_l, to_r)
-        got = torch.cat([from_l, from_r], dim=0)
-        ng = int(got.shape[0])
-        if n_owned + ng > self._bufs[0].shape[0]:
-            grown = [torch.empty((int((n_owned + ng) * 1.1) + 1024, 4), dtype=torch.float64, device=self.torch_device) for _ in range(4)]
-            for g, b in zip(grown, self._bufs):
-                g[:n_owned] = b[:n_owned]
-            self._bufs, self._buf_cap = grown, grown[0].shape[0]
-            bufs = self._bufs[:k]
-            A, B = bufs[0], bufs[1]
-        A[n_owned:n_owned + ng] = got[:, 0:4]
-        B[n_owned:n_owned + ng] = got[:, 4:8]
-        for b in bufs[2:]:
-            b[n_owned:n_owned + ng] = 0.0  # ghosts are never updated: no old state
-        s.mg_import(n_owned, ng, *([b.data_ptr() if n_owned + ng else None for b in bufs] + [None] * (4 - k)))
-        self.gid = torch.cat([gown, got[:, 8].to(torch.int64)])
-
-    def _halo(self, migrate, halo, with_old):
-        if not migrate and self.fast_ghost_refresh:
-            return self._halo_ghosts(halo, with_old)
-        rec, n_owned = self._export(with_old)
-        rec2, gid2, n_owned2 = exchange_records(rec, self.gid, n_owned, self.lo, self.hi, halo, migrate, self.axis, self.comm)
-        nf2 = rec2.shape[0]
-        parts = [rec2[:, 4 * k: 4 * k + 4].contiguous() for k in range(rec2.shape[1] // 4)]
-        ptrs = [p.data_ptr() if nf2 else None for p in parts] + [None] * (4 - len(parts))
-        self.solver.mg_import(n_owned2, nf2 - n_owned2, *ptrs)
-        self.gid = gid2
-        self._keep = parts  # alive until the next exchange (the import is asynchronous)
+        full = s.download(field)
+        full[: s.n_fluid] = values
+        s.upload(field, full)
 
     # ---- user surface ----
     def initialize(self):
         self.solver.initialize()
 
     def step(self, nsteps=1):
-        try:
-            return self.solver.step(nsteps)
-        except Exception:
-            if self._exc is not None:
-                exc, self._exc = self._exc, None
-                raise exc
-            raise
+        return self.solver.step(nsteps)
 
     def owned_state(self):
         """(gid, r, v, rho) of the particles this rank owns, as CPU tensors."""
-        with torch.cuda.stream(self._stream):
-            rec, n_owned = self._export(False)
-            rec, gid = rec[:n_owned].cpu(), self.gid[:n_owned].cpu()
-        D = self.dim
-        if D == 3:
-            return gid, rec[:, 0:3], rec[:, 4:7], rec[:, 3]
-        return gid, rec[:, 0:2], rec[:, 4:6], rec[:, 2]
+        gid, A, B = self.solver.mg_owned()
+        gid, A, B = torch.from_numpy(gid.copy()), torch.from_numpy(A.copy()), torch.from_numpy(B.copy())
+        if self.dim == 3:
+            return gid, A[:, 0:3], B[:, 0:3], A[:, 3]
+        return gid, A[:, 0:2], B[:, 0:2], A[:, 2]
 
     @property
     def n_owned(self):
