@@ -305,8 +305,20 @@ class Runner:
         prof = solver.profile_read() if profile else {}
         if profile:
             solver.profile(False)
+        self.rank_info = {"rank": self.rank, "ms_per_step": ms / steps, "kernel_ms_per_step": sum(v[1] for v in prof.values()) / steps if prof else None,
+                          "counts": self.solver.mg_counts(), "exchanges_migrated": self.solver.mg_stats()}
         ms = self.max_over_ranks(ms)
         return ms, clocks, launches, prof
+
+    def gather_rank_info(self):
+        """Per-rank step time, kernel-time sum and particle counts (owned, ghosts, walls) on rank 0."""
+        if self.world == 1:
+            return [self.rank_info]
+        import torch.distributed as dist
+
+        out = [None] * self.world
+        dist.all_gather_object(out, self.rank_info)
+        return out
 
     def e2e_steps(self, steps, warmup):
         """K steps through the C ABI with HOST buffers: every step uploads the state from
@@ -387,6 +399,7 @@ def run_ours(args, rank, local_rank, world):
 
     ms, clocks, launches, prof = run.timed_steps(args.steps, args.warmup)
     value = n_job * args.steps / (ms * 1e-3)
+    ranks = run.gather_rank_info()
     e2e_ms, h2d, d2h = run.e2e_steps(args.steps, args.warmup)
     e2e_value = n_job * args.steps / (e2e_ms * 1e-3)
 
@@ -427,14 +440,15 @@ def run_ours(args, rank, local_rank, world):
         sw = WORKLOADS[args.strong_workload]
         srun = Runner(args, 3, args.strong_n_col or sw["n_col"], rank, local_rank, world, "strong_x")
         s_steps = max(2, min(args.steps, 5))
-        s_ms, _, _, _ = srun.timed_steps(s_steps, 3, profile=False)
+        s_ms, _, _, _ = srun.timed_steps(s_steps, 3, profile=True)
         s_value = srun.n_total * s_steps / (s_ms * 1e-3)
+        s_ranks = srun.gather_rank_info()
         ref = strong_reference()
         same = bool(ref) and ref.get("n_total") == srun.n_total
         strong = {"workload": sw["label"] if not args.strong_n_col else f"3D dam break, n_col={args.strong_n_col}", "n_total": srun.n_total, "value": s_value, "unit": UNIT, "steps": s_steps, "ms_per_step": s_ms / s_steps,
                   "decomposition": f"{world} slabs of equally many lattice planes along x (fixed tank), halo 2R + dr_wall + dr",
                   "one_gpu_value": ref["value"] if same else None, "one_gpu_source": "profiles/strong_c5_1gpu.json" if same else None,
-                  "efficiency": (s_value / (world * ref["value"])) if same else None}
+                  "efficiency": (s_value / (world * ref["value"])) if same else None, "ranks": s_ranks}
         srun.close()
 
     if rank != 0:
@@ -469,6 +483,8 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in top[:12]},
     }
+    if world > 1:
+        out["ranks"] = ranks
     if strong is not None:
         out["strong"] = strong
     emit(json.dumps(out))

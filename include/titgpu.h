@@ -120,6 +120,10 @@ TITGPU_API unsigned long long titgpu_list_redos(const titgpu_ctx* ctx);
  * original particle order, columns ascending, self included. Call with
  * cols == NULL to obtain nnz. */
 TITGPU_API int titgpu_neighbors(titgpu_ctx* ctx, uint64_t* row_offsets, uint64_t* cols, size_t cap, size_t* nnz);
+/* ParticleMesh face adjacency, `mesh[domain, a]` (particle_mesh.hpp:74-82, 149-161;
+ * geom/face_search/grid_face_search.hpp:91-112): per particle the indices of the domain
+ * faces that intersect its support sphere, ascending. Same calling convention. */
+TITGPU_API int titgpu_face_neighbors(titgpu_ctx* ctx, uint64_t* row_offsets, uint64_t* cols, size_t cap, size_t* nnz);
 
 /* ---- Slab domain decomposition (one context per GPU / rank) -------------------
  * Replaces, across GPUs, what the reference's block partition does across

@@ -293,7 +293,7 @@ def test_gamma_interior_wall_corner_2d():
 def test_gamma_face_edge_corner_3d():
     # the evaluation point is moved off the wall by h^2 taken as a LENGTH (fluid_equations.hpp:187):
     # a small tank keeps that a small fraction of h
-    case = cases.dam_break_3d(6, H=0.06, wall_ratio=0.93, containment_margin=0.5)
+    case = cases.dam_break_3d(5, H=0.05, tank=(2.6, 2.4, 2.4), wall_ratio=0.93, containment_margin=0.5)
     s = oracle_lib.OracleSolver(3)
     oracle_lib.load_case(s, case)
     s.initialize()
@@ -307,18 +307,36 @@ def test_gamma_face_edge_corner_3d():
     face = (nwall == 1) & (dist_other > radius)
     edge = (nwall == 2) & (dist_other > radius)
     corner = nwall == 3
-    assert face.sum() > 50 and edge.sum() > 10 and corner.sum() == 8
+    assert face.sum() > 20 and edge.sum() > 10 and corner.sum() == 8
     assert np.abs(gamma[face] - 0.5).max() <= 0.03
     assert np.abs(gamma[edge] - 0.25).max() <= 0.03
     assert np.abs(gamma[corner] - 0.125).max() <= 0.03
 
 
+def still_tank_2d(n_col, H=0.6):
+    """A closed 2-D tank filled from wall to wall up to H with the hydrostatic (Tait) density."""
+    dr = H / n_col
+    PW, PH = dr * (n_col + 1), 2.0 * H
+    g, rho0 = 9.81, 1000.0
+    cs0 = 20 * math.sqrt(g * H)
+    verts, faces = cases.tessellate_2d(np.array([[0.0, PH], [PW, PH], [PW, 0.0], [0.0, 0.0]]), np.array([[0, 1], [1, 2], [2, 3], [3, 0]], dtype=np.uint64), dr)
+    cverts = np.array([[0.0, 0.0], [PW, 0.0], [PW, PH], [0.0, PH]])
+    cfaces = np.array([[0, 1], [1, 2], [2, 3], [3, 0]], dtype=np.uint64)
+    ii, jj = np.meshgrid(np.arange(n_col), np.arange(n_col), indexing="ij")
+    rf = dr * np.stack([ii.ravel() + 1.0, jj.ravel() + 1.0], axis=1)
+    r = np.concatenate([rf, verts])
+    nf, nx = len(rf), len(verts)
+    m, rho = np.full(nf + nx, rho0 * dr * dr), np.full(nf + nx, rho0)
+    p = rho0 * g * (dr * (n_col + 0.5) - rf[:, 1])  # free surface half a spacing above the top row
+    rho[:nf] = rho0 * (1.0 + 7.0 * p / (rho0 * cs0**2)) ** (1.0 / 7.0)
+    return cases.Case(2, nf, nx, r, m, rho, verts, faces, cverts, cfaces, g, 1e-3, cs0, rho0, 7.0, 2 * dr, dr, H, {"name": "still_tank_2d", "tank": (PW, PH)})
+
+
 def test_hydrostatic_column_is_in_equilibrium():
-    """A closed tank filled to the brim of the fluid block with the hydrostatic density
-    profile: interior accelerations vanish against g (pressure gradient balances gravity),
-    the density rate is that of the Ferrari diffusion of the profile alone (small)."""
-    n_col = 30
-    case = cases.dam_break_2d(n_col)
+    """A tank filled from wall to wall with the hydrostatic density profile: in the interior
+    the pair sums of the pressure term balance gravity to 1 % (the dam-break column itself is
+    NOT in equilibrium - its free side accelerates at t = 0)."""
+    case = still_tank_2d(30)
     s = oracle_lib.OracleSolver(2)
     oracle_lib.load_case(s, case)
     s.initialize()
@@ -326,10 +344,11 @@ def test_hydrostatic_column_is_in_equilibrium():
     nf = case.n_fluid
     rf = case.r[:nf]
     radius = 2.0 * case.h
-    # away from the free surfaces (top, right side of the column) and from the walls
-    inner = (rf[:, 0] > 2 * radius) & (rf[:, 0] < 2 * case.H - 6 * radius) & (rf[:, 1] > 2 * radius) & (rf[:, 1] < case.H - 6 * radius)
-    assert inner.sum() > 50
+    inner = (rf[:, 0] > radius) & (rf[:, 0] < case.meta["tank"][0] - radius) & (rf[:, 1] > radius) & (rf[:, 1] < case.H - 1.5 * radius)
+    assert inner.sum() > 300
     dv = s.download("dv_dt")[:nf][inner]
-    assert np.abs(dv).max() <= 0.05 * case.g
+    assert np.abs(dv).max() <= 0.02 * case.g
+    # without the pressure term the same particles would fall freely
+    assert np.abs(s.download("gamma")[:nf][inner] - 1.0).max() == 0.0
     drho = s.download("drho_dt")[:nf][inner]
-    assert np.abs(drho).max() * 1e-4 <= 1e-3 * case.rho0  # over a time step (1e-4 s) the density moves by < 1e-3 rho0
+    assert np.abs(drho).max() * 1e-4 <= 1e-4 * case.rho0  # over a time step (1e-4 s) the density moves by < 1e-4 rho0

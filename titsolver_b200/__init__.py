@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_mg_reserve", "titgpu_mg_counts",
     "titgpu_mg_set_slab", "titgpu_mg_set_gids", "titgpu_mg_attach_comm", "titgpu_mg_nccl_unique_id", "titgpu_mg_attach_nccl", "titgpu_mg_hub_create", "titgpu_mg_hub_destroy",
     "titgpu_mg_attach_hub", "titgpu_mg_detach", "titgpu_mg_download_owned", "titgpu_mg_upload_owned", "titgpu_mg_stats",
-    "titgpu_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
+    "titgpu_neighbors", "titgpu_face_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
     "titgpu_profile_enable", "titgpu_profile_reset", "titgpu_profile_count", "titgpu_profile_get", "titgpu_measure_fp64_peak",
 ]
 
@@ -67,6 +67,7 @@ def load_library() -> C.CDLL:
         getattr(lib, f).argtypes = [vp]
     lib.titgpu_step.argtypes = [vp, C.c_int, C.POINTER(d)]
     lib.titgpu_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
+    lib.titgpu_face_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
     lib.titgpu_set_outputs.argtypes = [vp, C.c_int]
     lib.titgpu_set_lists.argtypes = [vp, C.c_int]
     lib.titgpu_list_redos.argtypes = [vp]
@@ -274,14 +275,22 @@ class Solver:
         self._ck(self.lib.titgpu_mg_stats(self.h, C.byref(a), C.byref(b)), "titgpu_mg_stats")
         return int(a.value), int(b.value)
 
-    def neighbors(self):
+    def _csr(self, fn, what):
         nnz = C.c_size_t(0)
-        self._ck(self.lib.titgpu_neighbors(self.h, None, None, 0, C.byref(nnz)), "titgpu_neighbors")
+        self._ck(fn(self.h, None, None, 0, C.byref(nnz)), what)
         off = np.zeros(self.n + 1, np.uint64)
         cols = np.zeros(max(nnz.value, 1), np.uint64)
         u64p = C.POINTER(C.c_uint64)
-        self._ck(self.lib.titgpu_neighbors(self.h, off.ctypes.data_as(u64p), cols.ctypes.data_as(u64p), nnz.value, C.byref(nnz)), "titgpu_neighbors")
+        self._ck(fn(self.h, off.ctypes.data_as(u64p), cols.ctypes.data_as(u64p), nnz.value, C.byref(nnz)), what)
         return off, cols[: nnz.value]
+
+    def neighbors(self):
+        """Sorted neighbour rows (CSR, self included): `mesh[a]`."""
+        return self._csr(self.lib.titgpu_neighbors, "titgpu_neighbors")
+
+    def face_neighbors(self):
+        """Sorted rows of the domain faces meeting each particle's support sphere: `mesh[domain, a]`."""
+        return self._csr(self.lib.titgpu_face_neighbors, "titgpu_face_neighbors")
 
     def synchronize(self):
         self._ck(self.lib.titgpu_synchronize(self.h), "titgpu_synchronize")

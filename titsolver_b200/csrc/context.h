@@ -195,6 +195,7 @@ struct EngineVTable {
   int (*rhs_only)(Ctx&);
   int (*step)(Ctx&, int nsteps);
   int (*neighbors)(Ctx&, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz);
+  int (*face_neighbors)(Ctx&, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz);
   int (*download_state)(Ctx&, int field, double* dst_dev);  // unsort into original order
   int (*upload_state)(Ctx&, int field, const double* src_dev);
   // Slab decomposition: owned records in local-id order to / from device staging buffers.

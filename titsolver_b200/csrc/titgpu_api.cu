@@ -452,6 +452,13 @@ int titgpu_neighbors(titgpu_ctx* h, uint64_t* off, uint64_t* cols, size_t cap, s
   if (rc) return rc;
   TITGPU_LEAVE()
 }
+int titgpu_face_neighbors(titgpu_ctx* h, uint64_t* off, uint64_t* cols, size_t cap, size_t* nnz) {
+  TITGPU_ENTER(true)
+  if (!nnz) return fail(c, "nnz must not be null");
+  const int rc = c.vt->face_neighbors(c, off, cols, cap, nnz);
+  if (rc) return rc;
+  TITGPU_LEAVE()
+}
 int titgpu_synchronize(titgpu_ctx* h) {
   if (!h) return 1;
   Ctx& c = h->c;
