@@ -36,6 +36,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+REBALANCE_SHIFT = 30  # particle spacings a slab edge may move away from the initial equal-count cut
 METRIC = "WCSPH particle-updates/s"
 UNIT = "particle-updates/s"
 
@@ -250,8 +251,12 @@ class Runner:
             from titsolver_b200 import cases
             from titsolver_b200.slab import SlabSolver
 
-            case, edges, axis = cases.dam_break_3d_slab(n_col, world, rank, mode=mode)
+            # strong scaling: the wall pieces reach REBALANCE_SHIFT spacings beyond the usual margin, so that
+            # the slab edges can follow the measured cost (SlabSolver.rebalance)
+            case, edges, axis = cases.dam_break_3d_slab(n_col, world, rank, mode=mode, halo_cells=18 + (REBALANCE_SHIFT + 2 if mode == "strong_x" else 0))
             self.slab = SlabSolver(case, rank, world, axis=axis, edges=edges, device=local_rank, local=True)
+            self.extent = (case.dr, case.dr * 2 * n_col)  # the fluid column along x at t = 0
+            self.dr = case.dr
             self.solver = self.slab.solver
             self.n_fluid, self.n_fixed = case.meta["n_fluid_global"], case.meta["n_fixed_global"]
         else:
@@ -309,6 +314,26 @@ class Runner:
                           "counts": self.solver.mg_counts(), "exchanges_migrated": self.solver.mg_stats()}
         ms = self.max_over_ranks(ms)
         return ms, clocks, launches, prof
+
+    def rebalance(self, rounds=2, steps=2):
+        """Strong scaling: measure the kernel time per rank over `steps` steps, move the slab edges so
+        that every rank carries the same cost, let the next steps migrate the particles; `rounds` times.
+        (The end slabs carry the end walls and, the last one, the dry part of the tank.)"""
+        if self.slab is None or self.mode != "strong_x":
+            return None
+        solver, hist = self.solver, []
+        solver.set_outputs(0)
+        for _ in range(rounds):
+            solver.profile(True)
+            solver.profile_reset()
+            solver.step(steps)
+            cost = sum(v[1] for v in solver.profile_read().values()) / steps
+            solver.profile(False)
+            edges = self.slab.rebalance(cost, self.extent, max_shift=REBALANCE_SHIFT * self.dr)
+            hist.append({"cost_ms": cost, "edges_dr": [round(e / self.dr, 2) for e in edges[1:-1]]})
+            solver.step(1)  # migration to the new slabs
+        solver.set_outputs(2)
+        return hist
 
     def gather_rank_info(self):
         """Per-rank step time, kernel-time sum and particle counts (owned, ghosts, walls) on rank 0."""
@@ -394,6 +419,7 @@ def run_ours(args, rank, local_rank, world):
     mode = "strong_x" if strong_main else "weak_z"
     run = Runner(args, dim, n_col, rank, local_rank, world, mode)
     solver = run.solver
+    balance = run.rebalance() if not args.no_rebalance else None
     n_job, n_fluid, n_fixed = run.n_total, run.n_fluid, run.n_fixed  # particles of the whole job
     n = n_job / world  # per GPU (wall particles of the halos are not counted twice)
 
@@ -440,7 +466,8 @@ def run_ours(args, rank, local_rank, world):
         sw = WORKLOADS[args.strong_workload]
         srun = Runner(args, 3, args.strong_n_col or sw["n_col"], rank, local_rank, world, "strong_x")
         s_steps = max(2, min(args.steps, 5))
-        s_ms, _, _, _ = srun.timed_steps(s_steps, 3, profile=True)
+        s_balance = srun.rebalance() if not args.no_rebalance else None
+        s_ms, _, _, s_prof = srun.timed_steps(s_steps, 3, profile=True)
         s_value = srun.n_total * s_steps / (s_ms * 1e-3)
         s_ranks = srun.gather_rank_info()
         ref = strong_reference()
@@ -448,7 +475,8 @@ def run_ours(args, rank, local_rank, world):
         strong = {"workload": sw["label"] if not args.strong_n_col else f"3D dam break, n_col={args.strong_n_col}", "n_total": srun.n_total, "value": s_value, "unit": UNIT, "steps": s_steps, "ms_per_step": s_ms / s_steps,
                   "decomposition": f"{world} slabs of equally many lattice planes along x (fixed tank), halo 2R + dr_wall + dr",
                   "one_gpu_value": ref["value"] if same else None, "one_gpu_source": "profiles/strong_c5_1gpu.json" if same else None,
-                  "efficiency": (s_value / (world * ref["value"])) if same else None, "ranks": s_ranks}
+                  "efficiency": (s_value / (world * ref["value"])) if same else None, "ranks": s_ranks, "rebalance": s_balance,
+                  "kernels_ms_per_step_rank0": {k: round(v[1] / s_steps, 3) for k, v in sorted(s_prof.items(), key=lambda kv: -kv[1][1])}}
         srun.close()
 
     if rank != 0:
@@ -485,6 +513,8 @@ def run_ours(args, rank, local_rank, world):
     }
     if world > 1:
         out["ranks"] = ranks
+    if balance is not None:
+        out["rebalance"] = balance
     if strong is not None:
         out["strong"] = strong
     emit(json.dumps(out))
@@ -539,6 +569,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = the workload per GPU (tank N x deeper along z); strong = the workload itself cut into N slabs along x")
     ap.add_argument("--no-strong", action="store_true", help="N > 1, weak: skip the extra strong-scaling measurement (`strong` object)")
+    ap.add_argument("--no-rebalance", action="store_true", help="strong scaling: keep the equal-count slabs (no cost-based rebalancing)")
     ap.add_argument("--strong-workload", default="c5", choices=["c3", "c4", "c5"])
     ap.add_argument("--strong-n-col", type=int, default=0)
     args = ap.parse_args()

@@ -34,6 +34,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <tuple>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -65,6 +66,12 @@ public:
   auto num_faces() const noexcept -> std::size_t { return faces_.size(); }
   auto face_verts(std::size_t f) const noexcept -> const FaceVerts& { return faces_[f]; }
   auto face_verts() const noexcept -> std::span<const FaceVerts> { return faces_; }
+  /// The face as geometry: its vertices in order (the reference returns a Segment / Triangle built from them, tit/geom/surface.hpp).
+  auto face(std::size_t f) const noexcept -> std::array<V, Dim> {
+    std::array<V, Dim> out;
+    for (std::size_t k = 0; k < Dim; ++k) out[k] = verts_[faces_[f][k]];
+    return out;
+  }
   void append_face(const FaceVerts& f) { faces_.push_back(f); }
 private:
   std::vector<V> verts_;
@@ -519,6 +526,19 @@ public:
     cols.resize(nnz);
   }
 
+  /// Sorted face adjacency of the last search (`mesh[domain, a]`), CSR over original particle indices.
+  void face_neighbors_(std::vector<std::uint64_t>& offsets, std::vector<std::uint64_t>& cols) {
+    push_();
+    std::size_t nnz = 0;
+    call_(titgpu_face_neighbors(ctx_(), nullptr, nullptr, 0, &nnz), "titgpu_face_neighbors");
+    offsets.assign(size() + 1, 0);
+    cols.assign(std::max<std::size_t>(nnz, 1), 0);
+    call_(titgpu_face_neighbors(ctx_(), offsets.data(), cols.data(), nnz, &nnz), "titgpu_face_neighbors");
+    cols.resize(nnz);
+  }
+  /// Fixed particle k (= vertex k of the domain surface, wcsph.cpp:110-113).
+  auto fixed_at_(std::size_t k) noexcept { return ParticleView<ParticleArray>{*this, ranges_[1] + k}; }
+
   // ---- used by the equations / integrators (not part of the reference surface) ----
   auto ctx_() -> titgpu_ctx* {
     if (ctx_raw_ == nullptr) {
@@ -637,14 +657,54 @@ public:
     Array* arr = &a.array();
     return row | std::views::transform([arr](std::uint64_t b) { return ParticleView<Array>{*arr, std::size_t(b)}; });
   }
-  void invalidate_() noexcept { valid_ = false; }
+  /// Boundary faces adjacent to particle `a`, ascending: pairs of the face geometry and the
+  /// tuple of its vertex (fixed) particles (particle_mesh.hpp:74-82). With C++23 also `mesh[domain, a]`.
+  template<class Domain, class Array>
+  auto faces(const Domain& domain, ParticleView<Array> a) {
+    if (!fvalid_) { a.array().face_neighbors_(foffsets_, fcols_); fvalid_ = true; }
+    const auto row = std::span<const std::uint64_t>{fcols_}.subspan(foffsets_[a.index()], foffsets_[a.index() + 1] - foffsets_[a.index()]);
+    Array* arr = &a.array();
+    const Domain* dom = &domain;
+    return row | std::views::transform([arr, dom](std::uint64_t f) {
+             const auto& fv = dom->face_verts(std::size_t(f));
+             return [&]<std::size_t... I>(std::index_sequence<I...>) {
+               return std::pair{dom->face(std::size_t(f)), std::tuple{arr->fixed_at_(fv[I])...}};
+             }(std::make_index_sequence<std::tuple_size_v<std::remove_cvref_t<decltype(fv)>>>{});
+           });
+  }
+#if defined(__cpp_multidimensional_subscript)
+  template<class Domain, class Array>
+  auto operator[](const Domain& domain, ParticleView<Array> a) { return faces(domain, a); }
+#endif
+  /// Unique pairs (a, b), b < a, of adjacent particles in row order (particle_mesh.hpp:85-92, 228-240).
+  template<class Array>
+  auto pairs(Array& particles) {
+    if (!valid_) { particles.neighbors_(offsets_, cols_); valid_ = true; }
+    if (!pvalid_) {
+      pairs_.clear();
+      for (std::size_t a = 0; a + 1 < offsets_.size(); ++a)
+        for (std::uint64_t k = offsets_[a]; k < offsets_[a + 1] && cols_[k] < a; ++k) pairs_.emplace_back(a, std::size_t(cols_[k]));
+      pvalid_ = true;
+    }
+    Array* arr = &particles;
+    return std::views::all(pairs_) | std::views::transform([arr](const std::pair<std::size_t, std::size_t>& ab) {
+             return std::tuple{ParticleView<Array>{*arr, ab.first}, ParticleView<Array>{*arr, ab.second}};
+           });
+  }
+  /// The same pairs grouped into blocks (particle_mesh.hpp:95-105). The reference colours them
+  /// into 2T + 1 blocks so that T host threads never touch one particle at a time; the GPU pair
+  /// sums are gathers and need no colouring, so there is one block.
+  template<class Array>
+  auto block_pairs(Array& particles) { return std::views::single(pairs(particles)); }
+  void invalidate_() noexcept { valid_ = fvalid_ = pvalid_ = false; }
 private:
   Search search_;
   FaceSearch face_search_;
   Partition partition_;
   InterfacePartition interface_partition_;
-  bool valid_ = false;
-  std::vector<std::uint64_t> offsets_, cols_;
+  bool valid_ = false, fvalid_ = false, pvalid_ = false;
+  std::vector<std::uint64_t> offsets_, cols_, foffsets_, fcols_;
+  std::vector<std::pair<std::size_t, std::size_t>> pairs_;
 };
 template<class S, class F, class P, class I> ParticleMesh(S, F, P, I) -> ParticleMesh<S, F, P, I>;
 template<class S, class F> ParticleMesh(S, F) -> ParticleMesh<S, F>;

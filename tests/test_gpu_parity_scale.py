@@ -1,0 +1,250 @@
+"""GPU parity beyond the small resting cases of test_gpu_parity.py:
+
+* the BENCHMARK geometry itself (3-D lattice, wall spacing = particle spacing), with the
+  tolerance the reference's own arithmetic supports there - measured in the test by moving
+  every input by one ulp and re-running the oracle;
+* larger sizes (3-D n_col = 28: 90 890 particles; 2-D n_col = 200: 84 000 particles), one
+  step, all derived fields, multi-step drift;
+* EVOLVED states (300 GPU steps, plus a few particles thrown into the empty part of the
+  tank) with assertions that the interesting branches of fluid_equations.hpp:366-511 were
+  taken: free-surface density correction, splash rule, LU failure -> identity, the skipped
+  velocity correction near walls;
+* 3-D coverage of the remaining kernels, integrators and derived fields.
+"""
+import numpy as np
+import pytest
+
+import titsolver_b200 as tb
+from titsolver_b200 import cases
+
+pytestmark = pytest.mark.gpu
+
+STATE = ("r", "v", "rho")
+DERIVED = ("N", "L", "grad_v", "grad_rho", "dr", "phi", "rho_raw", "gamma", "grad_gamma", "drho_dt", "dv_dt", "p", "cs")
+FLUID_ONLY = ("drho_dt", "dv_dt")  # the reference accumulates garbage on fixed particles
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def rel_err_local(a, b, floor=1e-3):
+    """Per-particle relative error; values below `floor` x the field's maximum are measured against that floor."""
+    a, b = a.reshape(len(a), -1), b.reshape(len(b), -1)
+    scale = np.maximum(np.abs(b).max(axis=1), floor * max(np.abs(b).max(), 1e-300))
+    return float((np.abs(a - b).max(axis=1) / scale).max())
+
+
+def make_pair(oracle, case, kernel_id=4, eos_id=0, integrator_id=3):
+    g = tb.Solver(case.dim, kernel_id, eos_id, integrator_id)
+    c = oracle.OracleSolver(case.dim, kernel_id, eos_id, integrator_id)
+    tb.load_case(g, case)
+    oracle.load_case(c, case)
+    return g, c
+
+
+def fields_of(s, names, nf):
+    out = {}
+    for f in names:
+        a = s.download(f)
+        out[f] = a[:nf] if f in FLUID_ONLY else a
+    return out
+
+
+def one_ulp_sensitivity(oracle, case, names, run):
+    """How far the oracle's OWN results move when every coordinate moves by one ulp."""
+    c2 = cases.Case(**{**case.__dict__})
+    rng = np.random.default_rng(1)
+    sgn = rng.integers(0, 2, size=case.r.shape) * 2 - 1
+    c2.r = np.nextafter(case.r, case.r + sgn)
+    c2.verts = c2.r[case.n_fluid:].copy()
+    res = []
+    for cs_ in (case, c2):
+        s = oracle.OracleSolver(case.dim)
+        oracle.load_case(s, cs_)
+        s.initialize()
+        run(s)
+        res.append(fields_of(s, names, case.n_fluid))
+    return {f: rel_err(res[1][f], res[0][f]) for f in names}
+
+
+RHS_FIELDS = ("gamma", "grad_gamma", "rho", "p", "cs", "drho_dt", "dv_dt")
+
+
+@pytest.mark.parametrize("n_col", [12, 28])
+def test_rhs_parity_3d_benchmark_lattice(oracle, n_col):
+    """The geometry bench.py times (wall_ratio = 1, no jitter). Neighbours sit at exactly one
+    support radius and wall faces touch support spheres exactly, so the reference's results
+    are themselves only defined to the sensitivity measured here (grad_gamma of wall
+    particles ~3e-8, drho_dt ~1e-9); the GPU must stay within 10x of that, and within 1e-10
+    wherever the reference is that well defined."""
+    case = cases.dam_break_3d(n_col)
+    g, c = make_pair(oracle, case)
+    g.initialize(); c.initialize()
+    # neighbour sets and face sets are discrete: bit-exact even here
+    (og, cg), (oc, cc) = g.neighbors(), c.neighbors()
+    assert np.array_equal(og, oc) and np.array_equal(cg, cc)
+    (og, cg), (oc, cc) = g.face_neighbors(), c.face_neighbors()
+    assert np.array_equal(og, oc) and np.array_equal(cg, cc)
+    g.rhs_only(); c.rhs_only()
+    nf = case.n_fluid
+    a, b = fields_of(g, RHS_FIELDS, nf), fields_of(c, RHS_FIELDS, nf)
+    sens = one_ulp_sensitivity(oracle, case, RHS_FIELDS, lambda s: s.rhs_only())
+    assert sens["grad_gamma"] >= 1e-9, sens  # the degeneracy is real: one ulp moves wall grad_gamma by > 1e-9 relative
+    report = {}
+    for f in RHS_FIELDS:
+        err = rel_err(a[f], b[f])
+        report[f] = (err, sens[f])
+        assert err <= max(1e-10, 10.0 * sens[f]), (f, err, sens[f])
+        assert err <= 1e-6, (f, err)
+    # fluid particles away from the walls are generic: full accuracy, per particle
+    far = np.all((case.r[:nf] > 2.5 * 2 * case.h) & (case.r[:nf] < np.asarray(case.meta["tank"]) - 2.5 * 2 * case.h), axis=1)
+    if far.any():
+        assert np.array_equal(a["gamma"][:nf][far], b["gamma"][:nf][far])
+    print("lattice rhs parity (err, 1-ulp sensitivity):", report)
+
+
+def test_step_and_drift_3d_benchmark_lattice_n28(oracle):
+    """One SSPRK3 step with every derived field, then 5 steps of drift, on the n_col = 28 lattice."""
+    case = cases.dam_break_3d(28)
+    g, c = make_pair(oracle, case)
+    g.initialize(); c.initialize()
+    dt_g, dt_c = g.step(1), c.step(1)
+    assert abs(dt_g - dt_c) <= 1e-12 * dt_c
+    nf = case.n_fluid
+    for f in STATE:
+        assert rel_err(g.download(f), c.download(f)) <= 1e-10, f
+    a, b = fields_of(g, DERIVED, nf), fields_of(c, DERIVED, nf)
+    for f in DERIVED:
+        # wall particles' grad_gamma is the degenerate quantity (see the test above); everything the
+        # step actually consumes is generic to ~1e-9
+        tol = 1e-6 if f in ("grad_gamma", "N", "L", "grad_v", "grad_rho", "dr") else 1e-8
+        x, y = (a[f][:nf], b[f][:nf]) if f in ("N", "L", "grad_v", "grad_rho", "dr", "phi") else (a[f], b[f])
+        assert rel_err(x, y) <= tol, (f, rel_err(x, y))
+    assert np.array_equal(a["phi"][:nf] == 1.0, b["phi"][:nf] == 1.0)  # same free-surface classification
+    g.step(5); c.step(5)
+    for f, tol in (("r", 1e-9), ("v", 1e-6), ("rho", 1e-9)):
+        assert rel_err(g.download(f), c.download(f)) <= tol, f
+
+
+def test_step_and_drift_2d_n200(oracle):
+    """2-D at 84 000 particles: one step with all derived fields, then 50 steps of drift."""
+    case = cases.dam_break_2d(200)
+    g, c = make_pair(oracle, case)
+    g.initialize(); c.initialize()
+    g.step(1); c.step(1)
+    nf = case.n_fluid
+    for f in STATE:
+        assert rel_err(g.download(f), c.download(f)) <= 1e-10, f
+    a, b = fields_of(g, DERIVED, nf), fields_of(c, DERIVED, nf)
+    for f in DERIVED:
+        assert rel_err(a[f], b[f]) <= 1e-8, (f, rel_err(a[f], b[f]))
+    assert rel_err_local(a["dv_dt"], b["dv_dt"]) <= 1e-7
+    g.step(50); c.step(50)
+    for f, tol in (("r", 1e-8), ("v", 1e-5), ("rho", 1e-8)):
+        assert rel_err(g.download(f), c.download(f)) <= tol, f
+
+
+def evolved_pair(oracle, case, steps, spray):
+    """`steps` GPU steps, then `spray` fluid particles are thrown into the empty part of the tank
+    (one alone, the others in a tight group), and the state goes to a fresh oracle."""
+    g = tb.Solver(case.dim)
+    tb.load_case(g, case)
+    g.initialize()
+    g.step(steps)
+    st = {f: g.download(f) for f in ("r", "v", "rho", "m", "dv_dt")}
+    nf, dim = case.n_fluid, case.dim
+    tank = np.asarray(case.meta["tank"])
+    rng = np.random.default_rng(9)
+    ids = rng.choice(nf, size=spray, replace=False)
+    base = tank * 0.8
+    base[1] = tank[1] * 0.6
+    for k, i in enumerate(ids):
+        off = np.zeros(dim) if k == 0 else (5.0 * case.h + 0.3 * case.h * rng.uniform(-1, 1, size=dim))
+        st["r"][i] = base + off
+        st["v"][i] = rng.normal(size=dim)
+    c = oracle.OracleSolver(case.dim)
+    oracle.load_case(c, case)
+    c.initialize()
+    for s in (g, c):
+        for f in ("r", "v", "rho", "dv_dt"):
+            s.upload(f, st[f])
+    assert rel_err(c.download("m"), st["m"]) <= 1e-10  # wall masses were scaled by gamma once, on both sides
+    return g, c
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_evolved_state_takes_every_branch(oracle, dim):
+    case = cases.dam_break_2d(40) if dim == 2 else cases.dam_break_3d(10, wall_ratio=0.93, jitter=0.1)
+    g, c = evolved_pair(oracle, case, steps=300, spray=6)
+    dt_g, dt_c = g.step(1), c.step(1)
+    st = c.stats()
+    # every branch of apply_shifts / apply_free_surface_correction was taken on this state
+    assert st["lu_failed"] >= 1, st              # the lone particle: L is singular -> identity (fluid_equations.hpp:374-376)
+    assert st["splash"] >= 1, st                 # <= 8 / 26 neighbours -> free surface (:419-426)
+    assert st["near_surface"] >= 1 and st["shifted"] >= 1, st
+    assert st["shifted_no_v_correction"] >= 1, st  # shifted next to a wall: |gamma - 1| > tiny, no velocity correction (:468)
+    assert st["fs_corrected"] >= 1 and st["fs_candidates"] > st["fs_corrected"], st  # ratio <= 0.99 and ratio > 0.99 (:505)
+    assert abs(dt_g - dt_c) <= 1e-12 * dt_c
+    nf = case.n_fluid
+    for f in STATE:
+        assert rel_err(g.download(f), c.download(f)) <= 1e-10, f
+    a, b = fields_of(g, DERIVED, nf), fields_of(c, DERIVED, nf)
+    for f in DERIVED:
+        assert rel_err(a[f], b[f]) <= 1e-8, (f, rel_err(a[f], b[f]))
+    assert np.array_equal(a["phi"] == 1.0, b["phi"] == 1.0)
+    assert np.array_equal(a["rho_raw"] != g.download("rho"), b["rho_raw"] != c.download("rho"))  # the same particles were corrected
+
+
+# ---- 3-D coverage of the remaining options ----------------------------------------
+def case_3d(n_col=6):
+    return cases.dam_break_3d(n_col, wall_ratio=0.93, jitter=0.1)
+
+
+@pytest.mark.parametrize("kernel_id", [1, 3, 5])
+def test_rhs_parity_3d_remaining_kernels(oracle, kernel_id):
+    case = case_3d(5)
+    g, c = make_pair(oracle, case, kernel_id=kernel_id)
+    g.initialize(); c.initialize()
+    g.rhs_only(); c.rhs_only()
+    a, b = fields_of(g, RHS_FIELDS, case.n_fluid), fields_of(c, RHS_FIELDS, case.n_fluid)
+    for f in RHS_FIELDS:
+        assert rel_err(a[f], b[f]) <= 1e-10, f
+
+
+@pytest.mark.parametrize("integrator_id", [0, 1, 2])
+def test_one_step_3d_other_integrators(oracle, integrator_id):
+    case = case_3d(6)
+    g, c = make_pair(oracle, case, integrator_id=integrator_id)
+    g.initialize(); c.initialize()
+    dt_g, dt_c = g.step(1), c.step(1)
+    assert abs(dt_g - dt_c) <= 1e-12 * dt_c
+    for f in STATE:
+        assert rel_err(g.download(f), c.download(f)) <= 1e-10, f
+
+
+def test_one_step_3d_all_derived_fields_and_drift(oracle):
+    case = case_3d(8)
+    g, c = make_pair(oracle, case)
+    g.initialize(); c.initialize()
+    g.step(1); c.step(1)
+    nf = case.n_fluid
+    a, b = fields_of(g, DERIVED, nf), fields_of(c, DERIVED, nf)
+    for f in DERIVED:
+        assert rel_err(a[f], b[f]) <= 1e-9, (f, rel_err(a[f], b[f]))
+    assert rel_err_local(a["dv_dt"], b["dv_dt"]) <= 1e-8
+    g.step(20); c.step(20)
+    for f in STATE:
+        assert rel_err(g.download(f), c.download(f)) <= 1e-7, f
+
+
+@pytest.mark.parametrize("case_name", ["2d", "3d_generic", "3d_lattice", "3d_fine_walls"])
+def test_face_adjacency_is_bit_exact(oracle, case_name):
+    """`mesh[domain, a]` (particle_mesh.hpp:74-82, 149-161): the sorted face rows equal the oracle's."""
+    case = {"2d": lambda: cases.dam_break_2d(40), "3d_generic": lambda: case_3d(6), "3d_lattice": lambda: cases.dam_break_3d(8),
+            "3d_fine_walls": lambda: cases.dam_break_3d(5, wall_ratio=0.43, jitter=0.1)}[case_name]()
+    g, c = make_pair(oracle, case)
+    (og, cg), (oc, cc) = g.face_neighbors(), c.face_neighbors()
+    assert np.array_equal(og, oc), "row offsets differ"
+    assert np.array_equal(cg, cc), "face columns differ"
+    assert len(cg) > 0 and np.diff(og.astype(np.int64))[: case.n_fluid].max() > 0

@@ -182,6 +182,51 @@ def local_surface(verts: np.ndarray, faces: np.ndarray, axis: int, lo: float, hi
     return verts[vid], inv.reshape(f.shape).astype(np.uint64), vid
 
 
+def rebalanced_edges(edges, costs, x_min, x_max, min_width, max_shift=None, ref_edges=None):
+    """New slab edges that equalise a measured per-rank cost (e.g. the kernel time of the
+    last steps). The cost of rank i is taken as uniformly spread over its slab - for the end
+    slabs over the part that holds particles, [x_min, edges[1]) and [edges[-2], x_max] - and
+    the new interior edges are the k / N quantiles of the resulting piecewise-linear
+    cumulative cost. Every slab keeps at least `min_width` (the halo: ghosts come from
+    adjacent slabs only) and no edge ends up farther than `max_shift` from `ref_edges` (default:
+    `edges`) - what the rank-local wall pieces were cut for. The role of the reference's partitioners
+    (geom/partition/sort_partition.hpp:25-75: equal COUNTS along a sort key) with measured
+    cost in place of counts. Pure function: the same on every rank."""
+    world = len(edges) - 1
+    if world == 1:
+        return list(edges)
+    knots = [float(x_min)] + [float(e) for e in edges[1:-1]] + [float(x_max)]
+    for a, b in zip(knots[:-1], knots[1:]):
+        if not a < b:
+            raise ValueError("rebalanced_edges: particles do not span every slab")
+    cum = np.concatenate([[0.0], np.cumsum(np.asarray(costs, dtype=np.float64))])
+    if not cum[-1] > 0:
+        return list(edges)
+    targets = cum[-1] * np.arange(1, world) / world
+    new = np.interp(targets, cum, knots)
+    out = [-math.inf]
+    for k in range(1, world):
+        e = float(new[k - 1])
+        if max_shift is not None:
+            ref = (ref_edges or edges)[k]
+            e = min(max(e, ref - max_shift), ref + max_shift)
+        lo_prev = out[-1] if k > 1 else knots[0]
+        e = max(e, lo_prev + min_width)
+        out.append(e)
+    # keep the tail feasible as well (walk back from the right end)
+    hi_next = knots[-1]
+    for k in range(world - 1, 0, -1):
+        out[k] = min(out[k], hi_next - min_width)
+        hi_next = out[k]
+    out.append(math.inf)
+    for a, b in zip(out[1:-2], out[2:-1]):
+        if not b - a >= min_width * (1 - 1e-12):
+            raise ValueError("rebalanced_edges: too many slabs for this extent")
+    if not (out[1] > knots[0] and out[-2] < knots[-1]):
+        raise ValueError("rebalanced_edges: too many slabs for this extent")
+    return out
+
+
 def halo_width(case, kernel_id=4, margin_dr=1.0):
     """(halo, R, dw): ghost-layer width 2 R + dw + margin, support radius, longest wall-face edge."""
     R = 2.0 * case.h if kernel_id not in (1, 2) else (2.5 if kernel_id == 1 else 3.0) * case.h
@@ -220,7 +265,8 @@ class SlabSolver:
             fluid_total = nf if fluid_total is None else fluid_total
         elif fluid_total is None:
             fluid_total = case.meta.get("n_fluid_global", -1)
-        self.layout = SlabLayout(axis, edges, halo, halo)
+        self.layout = SlabLayout(axis, list(edges), halo, halo)
+        self.edges0 = list(edges)  # the edges the rank-local wall pieces were cut for
         lo, hi = self.layout.bounds(rank)
         self.lo, self.hi = lo, hi
         if not local:
@@ -252,6 +298,7 @@ class SlabSolver:
         s.upload("m", mass)
         s.upload("rho", rho)
         s.mg_set_gids(gid)
+        self.fluid_total = fluid_total
         s.mg_set_slab(axis, lo, hi, halo, fluid_total)
         if world > 1:
             if hub is not None:
@@ -260,6 +307,22 @@ class SlabSolver:
                 box = [tb.nccl_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(box, src=0, group=group)
                 s.mg_attach_nccl(box[0], rank, world)
+
+    def rebalance(self, cost, extent, max_shift=None, group=None):
+        """Equalise `cost` (this rank's measured time per step, any unit) over the ranks by moving
+        the slab edges (`rebalanced_edges`); the next step migrates the particles that changed
+        slab. `extent` = (x_min, x_max) of the fluid along the slab axis, the same on every rank.
+        Collective over torch.distributed (all ranks call it with their own cost)."""
+        costs = [None] * self.world
+        dist.all_gather_object(costs, float(cost), group=group)
+        edges = rebalanced_edges(self.layout.edges, costs, extent[0], extent[1], self.layout.w_rhs, max_shift, self.edges0)
+        self.set_edges(edges)
+        return edges
+
+    def set_edges(self, edges):
+        self.layout.edges = list(edges)
+        self.lo, self.hi = self.layout.bounds(self.rank)
+        self.solver.mg_set_slab(self.axis, self.lo, self.hi, self.layout.w_rhs, self.fluid_total)
 
     def upload_owned_field(self, field, values):
         """Set `field` ("v", "rho", ...) of the owned particles before the first step
