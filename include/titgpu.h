@@ -116,6 +116,15 @@ TITGPU_API int titgpu_set_outputs(titgpu_ctx* ctx, int level);
 TITGPU_API int titgpu_set_lists(titgpu_ctx* ctx, int on);
 TITGPU_API unsigned long long titgpu_list_redos(const titgpu_ctx* ctx);
 
+/* Shared-memory-staged kernel-sum pass (3-D, kernels of support radius 2h; default OFF;
+ * titgpu_set_tiles(ctx, 1) or the environment TITGPU_TILES=1 turns it on): one block per tile of
+ * 2 x 2 x 2 search cells stages the 36 contiguous record runs of the 6 x 6 x 6 cells around it
+ * in shared memory with cp.async.bulk + mbarrier and evaluates the pair sums from there
+ * (csrc/tile.cuh). Same neighbour sets, same results to rounding (the order of the sums
+ * differs). Measured on B200 it is slower than the default gather traversal (one block of 16
+ * warps per SM cannot hide the FP64 latency): kept as an option. */
+TITGPU_API int titgpu_set_tiles(titgpu_ctx* ctx, int on);
+
 /* ParticleMesh adjacency (particle_mesh.hpp:67-72, 137-147): CSR, rows in
  * original particle order, columns ascending, self included. Call with
  * cols == NULL to obtain nnz. */

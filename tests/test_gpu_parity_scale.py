@@ -51,7 +51,7 @@ def fields_of(s, names, nf):
     return out
 
 
-def one_ulp_sensitivity(oracle, case, names, run):
+def one_ulp_sensitivity(oracle, case, names, run, **kw):
     """How far the oracle's OWN results move when every coordinate moves by one ulp."""
     c2 = cases.Case(**{**case.__dict__})
     rng = np.random.default_rng(1)
@@ -60,7 +60,7 @@ def one_ulp_sensitivity(oracle, case, names, run):
     c2.verts = c2.r[case.n_fluid:].copy()
     res = []
     for cs_ in (case, c2):
-        s = oracle.OracleSolver(case.dim)
+        s = oracle.OracleSolver(case.dim, **kw)
         oracle.load_case(s, cs_)
         s.initialize()
         run(s)
@@ -138,7 +138,10 @@ def test_step_and_drift_2d_n200(oracle):
         assert rel_err(g.download(f), c.download(f)) <= 1e-10, f
     a, b = fields_of(g, DERIVED, nf), fields_of(c, DERIVED, nf)
     for f in DERIVED:
-        assert rel_err(a[f], b[f]) <= 1e-8, (f, rel_err(a[f], b[f]))
+        # N, L and the gradients are renormalised by (L^T)^-1 and N by its own length: ill-conditioned
+        # where the raw sums nearly cancel (the interior of the lattice)
+        tol = 1e-6 if f in ("N", "L", "grad_v", "grad_rho", "dr") else 1e-8
+        assert rel_err(a[f], b[f]) <= tol, (f, rel_err(a[f], b[f]))
     assert rel_err_local(a["dv_dt"], b["dv_dt"]) <= 1e-7
     g.step(50); c.step(50)
     for f, tol in (("r", 1e-8), ("v", 1e-5), ("rho", 1e-8)):
@@ -157,11 +160,11 @@ def evolved_pair(oracle, case, steps, spray):
     tank = np.asarray(case.meta["tank"])
     rng = np.random.default_rng(9)
     ids = rng.choice(nf, size=spray, replace=False)
-    base = tank * 0.8
-    base[1] = tank[1] * 0.6
+    lone, group = tank * 0.85, tank * 0.65  # both in the dry part of the tank, well inside it
+    lone[1] = group[1] = tank[1] * 0.6
+    lone[-1] = group[-1] = tank[-1] * 0.5
     for k, i in enumerate(ids):
-        off = np.zeros(dim) if k == 0 else (5.0 * case.h + 0.3 * case.h * rng.uniform(-1, 1, size=dim))
-        st["r"][i] = base + off
+        st["r"][i] = lone if k == 0 else group + 0.4 * case.h * rng.uniform(-1, 1, size=dim)
         st["v"][i] = rng.normal(size=dim)
     c = oracle.OracleSolver(case.dim)
     oracle.load_case(c, case)
@@ -176,7 +179,7 @@ def evolved_pair(oracle, case, steps, spray):
 @pytest.mark.parametrize("dim", [2, 3])
 def test_evolved_state_takes_every_branch(oracle, dim):
     case = cases.dam_break_2d(40) if dim == 2 else cases.dam_break_3d(10, wall_ratio=0.93, jitter=0.1)
-    g, c = evolved_pair(oracle, case, steps=300, spray=6)
+    g, c = evolved_pair(oracle, case, steps=300, spray=10)
     dt_g, dt_c = g.step(1), c.step(1)
     st = c.stats()
     # every branch of apply_shifts / apply_free_surface_correction was taken on this state
@@ -208,8 +211,14 @@ def test_rhs_parity_3d_remaining_kernels(oracle, kernel_id):
     g.initialize(); c.initialize()
     g.rhs_only(); c.rhs_only()
     a, b = fields_of(g, RHS_FIELDS, case.n_fluid), fields_of(c, RHS_FIELDS, case.n_fluid)
+    # The reference's 3-D boundary integrals of the quartic spline (kernel 1) are ill-conditioned:
+    # one ulp on the inputs moves ITS gamma by 1e-6 and grad_gamma by 1e-8 on this generic case
+    # (kernels 3 and 5: 1e-14 .. 1e-12). The bound follows the measured sensitivity.
+    sens = one_ulp_sensitivity(oracle, case, RHS_FIELDS, lambda s: s.rhs_only(), kernel_id=kernel_id)
+    if kernel_id != 1:
+        assert max(sens.values()) <= 1e-11, sens
     for f in RHS_FIELDS:
-        assert rel_err(a[f], b[f]) <= 1e-10, f
+        assert rel_err(a[f], b[f]) <= max(1e-10, 10.0 * sens[f]), (f, rel_err(a[f], b[f]), sens[f])
 
 
 @pytest.mark.parametrize("integrator_id", [0, 1, 2])
@@ -248,3 +257,34 @@ def test_face_adjacency_is_bit_exact(oracle, case_name):
     assert np.array_equal(og, oc), "row offsets differ"
     assert np.array_equal(cg, cc), "face columns differ"
     assert len(cg) > 0 and np.diff(og.astype(np.int64))[: case.n_fluid].max() > 0
+
+
+@pytest.mark.parametrize("lattice", [False, True])
+def test_shared_memory_staged_pass_equals_the_gather_traversal(oracle, lattice):
+    """titgpu_set_tiles: the tile pass (cp.async.bulk staging, csrc/tile.cuh) and the default
+    gather traversal see the same neighbours; results agree to the order of the sums, and the
+    tile pass meets the oracle on its own."""
+    case = cases.dam_break_3d(14) if lattice else cases.dam_break_3d(10, wall_ratio=0.93, jitter=0.1)
+    res = []
+    for tiles in (True, False):
+        g = tb.Solver(3)
+        g.set_tiles(tiles)
+        tb.load_case(g, case)
+        g.initialize()
+        g.profile(True)
+        g.rhs_only()
+        out = {f: g.download(f)[: case.n_fluid] for f in ("drho_dt", "dv_dt")}
+        names = " ".join(g.profile_read())
+        assert ("k_rhs_tile" in names) == tiles, names
+        g.step(2)
+        out.update({f: g.download(f) for f in STATE})
+        res.append(out)
+    for f in res[0]:
+        assert rel_err(res[0][f], res[1][f]) <= 1e-11, f
+    if not lattice:
+        c = oracle.OracleSolver(3)
+        oracle.load_case(c, case)
+        c.initialize()
+        c.step(2)
+        for f in STATE:
+            assert rel_err(res[0][f], c.download(f)) <= 1e-10, f

@@ -30,7 +30,7 @@ FIELDS = {
 ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
-    "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_mg_reserve", "titgpu_mg_counts",
+    "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_set_tiles", "titgpu_mg_reserve", "titgpu_mg_counts",
     "titgpu_mg_set_slab", "titgpu_mg_set_gids", "titgpu_mg_attach_comm", "titgpu_mg_nccl_unique_id", "titgpu_mg_attach_nccl", "titgpu_mg_hub_create", "titgpu_mg_hub_destroy",
     "titgpu_mg_attach_hub", "titgpu_mg_detach", "titgpu_mg_download_owned", "titgpu_mg_upload_owned", "titgpu_mg_stats",
     "titgpu_neighbors", "titgpu_face_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
@@ -70,6 +70,7 @@ def load_library() -> C.CDLL:
     lib.titgpu_face_neighbors.argtypes = [vp, u64p, u64p, sz, C.POINTER(sz)]
     lib.titgpu_set_outputs.argtypes = [vp, C.c_int]
     lib.titgpu_set_lists.argtypes = [vp, C.c_int]
+    lib.titgpu_set_tiles.argtypes = [vp, C.c_int]
     lib.titgpu_list_redos.argtypes = [vp]
     lib.titgpu_list_redos.restype = C.c_ulonglong
     lib.titgpu_mg_reserve.argtypes = [vp, sz]
@@ -218,6 +219,10 @@ class Solver:
     def set_lists(self, on):
         """Step-persistent candidate lists on / off (titgpu_set_lists)."""
         self._ck(self.lib.titgpu_set_lists(self.h, int(bool(on))), "titgpu_set_lists")
+
+    def set_tiles(self, on):
+        """Shared-memory-staged kernel-sum pass on / off (titgpu_set_tiles; 3-D, radius-2h kernels)."""
+        self._ck(self.lib.titgpu_set_tiles(self.h, int(bool(on))), "titgpu_set_tiles")
 
     @property
     def list_redos(self):

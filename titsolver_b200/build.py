@@ -24,7 +24,7 @@ LIB = os.path.join(HERE, "libtitgpu" + ("_" + VARIANT if VARIANT else "") + ".so
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-ccbin", "/usr/bin/g++"]
-HEADERS = ["common.cuh", "context.h", "engine.cuh", "mg.cuh", "mg_transport.h", "sph_kernel.cuh", "kernels_gen.cuh", "../../include/titgpu.h"]
+HEADERS = ["common.cuh", "context.h", "engine.cuh", "mg.cuh", "tile.cuh", "mg_transport.h", "sph_kernel.cuh", "kernels_gen.cuh", "../../include/titgpu.h"]
 
 
 def _newer(target, deps):

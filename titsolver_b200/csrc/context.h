@@ -112,6 +112,11 @@ struct Ctx {
   DBuf gamma_w, gg_w, wsum;      // wall pass: gamma, grad gamma, face sums of the consumer
   DBuf gamma_s, N_s, phi_s, phi2_s, dr_s, gv_s, gr_s, fs_flag;  // post-integration scratch
 
+  // Tiles of the shared-memory-staged pair passes (tile.cuh): non-empty tiles of the current sort.
+  bool tiles_enabled = false, tiles_valid = false;  // TITGPU_TILES=1 / titgpu_set_tiles: measured slower than the gather traversal on B200, kept as an option
+  DBuf tile_list, tile_count;                      // tile ids | {count, work cursor}
+  int tile_nty = 0, tile_ntz = 0;
+
   // Hash / sort scratch.
   DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp, cell_fs, cell_fluid;
 

@@ -23,6 +23,7 @@ template<int D> struct FaceFrame;
 // 2-D segment: a, unit normal n = normalize((ba.y, -ba.x)), unit tangent e, length.
 template<> struct FaceFrame<2> {
   double a[2], n[2], e[2], len;
+  double b[2];          // second vertex (world coordinates: the exact intersection test)
   double ctr[2];        // mean of the vertices (r_s of the face)
   double lo[2], hi[2];  // bbox
   unsigned v[2];        // vertex (== fixed particle) indices
@@ -35,7 +36,9 @@ template<> struct FaceFrame<3> {
   double et[3][2], elen[3];  // unit tangent and length of the edges a->b, b->c, c->a in the (e1, e2) frame
   double ctr[3];
   double lo[3], hi[3];
+  double b[3], c[3];    // second / third vertex in world coordinates (the exact intersection test)
   unsigned v[3];
+  int degen;            // triangle_degeneracy(): the reference clamps a near-zero-area triangle to its longest edge
 };
 
 template<int KID>
@@ -295,54 +298,87 @@ struct SphKernel {
 };
 
 // Exact sphere/face intersection test of the reference face search
-// (geom/segment.hpp:92-112, geom/triangle.hpp:116-186): bbox overlap, then
-// closest point on the face within the radius.
+// (geom/segment.hpp:92-112, geom/triangle.hpp:116-186, geom/bsphere.hpp:47-53): bbox
+// overlap, then the closest point on the face (clamp) within the radius, inclusive. The
+// arithmetic is the reference's own, operation by operation and without FMA contraction,
+// on the world coordinates of the vertices: on the benchmark lattice faces TOUCH support
+// spheres exactly, and membership must not depend on how the closest point is computed.
+// Mirrored quirk: `is_tiny(area())` / `is_tiny(norm2(ba))` compare dimensional quantities
+// with the absolute tiny = 6e-6, so a fine wall mesh (triangle area below 6e-6, e.g. C5) is
+// clamped to its longest EDGE and a short segment to its first vertex.
+template<int DD> TIT_HD Vec<DD> clamp_to_segment(const Vec<DD>& a, const Vec<DD>& b, const Vec<DD>& p, double tiny) {
+  const Vec<DD> ba = xsubv(b, a);
+  const double len2 = xdot(ba, ba);
+  if (fabs(len2) <= tiny) return a;
+  const double t = xdot(xsubv(p, a), ba) / len2;
+  if (t < 0.0) return a;
+  if (t > 1.0) return b;
+  Vec<DD> q;
+  for (int d = 0; d < DD; ++d) q[d] = xadd(a[d], xmul(t, ba[d]));
+  return q;
+}
 TIT_HD bool face_intersects(const FaceFrame<2>& f, const Vec<2>& c, double radius, double radius2, double tiny) {
   for (int d = 0; d < 2; ++d)
     if (!(c[d] - radius <= f.hi[d] && f.lo[d] <= c[d] + radius)) return false;
-  // clamp(): a + t * ba with t in [0, 1]; ba = e * len.
-  const double px = c[0] - f.a[0], py = c[1] - f.a[1];
-  const double len2 = f.len * f.len;
-  double qx, qy;
-  if (fabs(len2) <= tiny) {
-    qx = f.a[0]; qy = f.a[1];
-  } else {
-    const double bax = f.e[0] * f.len, bay = f.e[1] * f.len;
-    const double t = (px * bax + py * bay) / len2;
-    if (t < 0.0) { qx = f.a[0]; qy = f.a[1]; }
-    else if (t > 1.0) { qx = f.a[0] + bax; qy = f.a[1] + bay; }
-    else { qx = f.a[0] + t * bax; qy = f.a[1] + t * bay; }
-  }
-  const double dx = qx - c[0], dy = qy - c[1];
-  return dx * dx + dy * dy <= radius2;
+  Vec<2> a, b;
+  for (int d = 0; d < 2; ++d) { a[d] = f.a[d]; b[d] = f.b[d]; }
+  const Vec<2> x = xsubv(clamp_to_segment<2>(a, b, c, tiny), c);
+  return xdot(x, x) <= radius2;
 }
 
+// 0: a proper triangle; 1 / 2 / 3: is_tiny(area) and the longest edge is ab / bc / ac (triangle.hpp:118-135).
+TIT_HD int triangle_degeneracy(const Vec<3>& a, const Vec<3>& b, const Vec<3>& c, double tiny) {
+  const Vec<3> ba = xsubv(b, a), ca = xsubv(c, a), cb = xsubv(c, b);
+  Vec<3> w;
+  w[0] = xmul(xsub(xmul(ba[1], ca[2]), xmul(ba[2], ca[1])), 0.5);
+  w[1] = xmul(xsub(xmul(ba[2], ca[0]), xmul(ba[0], ca[2])), 0.5);
+  w[2] = xmul(xsub(xmul(ba[0], ca[1]), xmul(ba[1], ca[0])), 0.5);
+  if (!(fabs(sqrt(xdot(w, w))) <= tiny)) return 0;
+  const double ab = xdot(ba, ba), bc = xdot(cb, cb), ca2 = xdot(ca, ca);
+  if (ab >= bc && ab >= ca2) return 1;
+  if (bc >= ca2) return 2;
+  return 3;
+}
 TIT_HD bool face_intersects(const FaceFrame<3>& f, const Vec<3>& p, double radius, double radius2, double tiny) {
   for (int d = 0; d < 3; ++d)
     if (!(p[d] - radius <= f.hi[d] && f.lo[d] <= p[d] + radius)) return false;
-  // Work in the triangle frame: a = (0,0), b = (bx,0), c = (cx,cy), point
-  // (u, v, w) with w the plane distance. Closest point on the triangle follows
-  // the region walk of geom/triangle.hpp:137-181 (Ericson), evaluated in-plane.
-  const double x = p[0] - f.a[0], y = p[1] - f.a[1], z = p[2] - f.a[2];
-  const double u = x * f.e1[0] + y * f.e1[1] + z * f.e1[2];
-  const double v = x * f.e2[0] + y * f.e2[1] + z * f.e2[2];
-  const double w = x * f.n[0] + y * f.n[1] + z * f.n[2];
-  const double bx = f.bx, cx = f.cx, cy = f.cy;
-  (void)tiny;
-  double qu, qv;
-  const double d1 = bx * u, d2 = cx * u + cy * v;
-  const double d3 = bx * (u - bx), d4 = cx * (u - bx) + cy * v;
-  const double d5 = bx * (u - cx), d6 = cx * (u - cx) + cy * (v - cy);
-  const double vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
-  if (d1 <= 0.0 && d2 <= 0.0) { qu = 0; qv = 0; }
-  else if (d3 >= 0.0 && d4 <= d3) { qu = bx; qv = 0; }
-  else if (d6 >= 0.0 && d5 <= d6) { qu = cx; qv = cy; }
-  else if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) { const double t = d1 / (d1 - d3); qu = t * bx; qv = 0; }
-  else if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { const double t = d2 / (d2 - d6); qu = t * cx; qv = t * cy; }
-  else if (va <= 0.0 && d4 >= d3 && d5 >= d6) { const double t = (d4 - d3) / ((d4 - d3) + (d5 - d6)); qu = bx + t * (cx - bx); qv = t * cy; }
-  else { const double s = 1.0 / (va + vb + vc); const double tv = vb * s, tw = vc * s; qu = tv * bx + tw * cx; qv = tw * cy; }
-  const double du = qu - u, dv = qv - v;
-  return du * du + dv * dv + w * w <= radius2;
+  Vec<3> a, b, c, q;
+  for (int d = 0; d < 3; ++d) { a[d] = f.a[d]; b[d] = f.b[d]; c[d] = f.c[d]; }
+  if (f.degen) {
+    q = f.degen == 1 ? clamp_to_segment<3>(a, b, p, tiny) : f.degen == 2 ? clamp_to_segment<3>(b, c, p, tiny) : clamp_to_segment<3>(a, c, p, tiny);
+  } else {
+    // Ericson's region walk, geom/triangle.hpp:137-181.
+    const Vec<3> ba = xsubv(b, a), ca = xsubv(c, a);
+    const Vec<3> pa = xsubv(p, a);
+    const double d1 = xdot(ba, pa), d2 = xdot(ca, pa);
+    const Vec<3> pb = xsubv(p, b);
+    const double d3 = xdot(ba, pb), d4 = xdot(ca, pb);
+    const Vec<3> pc = xsubv(p, c);
+    const double d5 = xdot(ba, pc), d6 = xdot(ca, pc);
+    const double vc = xsub(xmul(d1, d4), xmul(d3, d2));
+    const double vb = xsub(xmul(d5, d2), xmul(d1, d6));
+    const double va = xsub(xmul(d3, d6), xmul(d5, d4));
+    if (d1 <= 0.0 && d2 <= 0.0) q = a;
+    else if (d3 >= 0.0 && d4 <= d3) q = b;
+    else if (d6 >= 0.0 && d5 <= d6) q = c;
+    else if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+      const double t = d1 / xsub(d1, d3);
+      for (int d = 0; d < 3; ++d) q[d] = xadd(a[d], xmul(t, ba[d]));
+    } else if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+      const double t = d2 / xsub(d2, d6);
+      for (int d = 0; d < 3; ++d) q[d] = xadd(a[d], xmul(t, ca[d]));
+    } else if (va <= 0.0 && d4 >= d3 && d5 >= d6) {
+      const double t = xsub(d4, d3) / xadd(xsub(d4, d3), xsub(d5, d6));
+      const Vec<3> cb = xsubv(c, b);
+      for (int d = 0; d < 3; ++d) q[d] = xadd(b[d], xmul(t, cb[d]));
+    } else {
+      const double den = xadd(xadd(va, vb), vc);
+      const double v = vb / den, w = vc / den;
+      for (int d = 0; d < 3; ++d) q[d] = xadd(xadd(a[d], xmul(v, ba[d])), xmul(w, ca[d]));
+    }
+  }
+  const Vec<3> x = xsubv(q, p);
+  return xdot(x, x) <= radius2;
 }
 
 }  // namespace titgpu

@@ -125,6 +125,7 @@ int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_
   TIT_CUDA_OK(c, cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
   c.prm.eos = eos_id;
   if (const char* e = std::getenv("TITGPU_LISTS")) c.lists_enabled = e[0] != '0';
+  if (const char* e = std::getenv("TITGPU_TILES")) c.tiles_enabled = e[0] != '0';
   return 0;
 }
 
@@ -137,7 +138,7 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (DBuf& b : c.buf_orig) b.release();
   for (DBuf* b : {&c.C, &c.F, &c.gamma_w, &c.gg_w, &c.wsum, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.fs_flag, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm,
                   &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.cell_fs, &c.cell_fluid, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.ftwin, &c.fterm, &c.favg, &c.ww_faces, &c.ww_sref, &c.ww_items, &c.ww_val, &c.ww_rims, &c.ww_val2, &c.ww_act, &c.ww_ovf, &c.ww_x2, &c.ww_cur, &c.ww_list, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
-                  &c.rho_fx, &c.p_fx, &c.staging, &c.scalars, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
+                  &c.rho_fx, &c.p_fx, &c.staging, &c.scalars, &c.tile_list, &c.tile_count, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
     b->release();
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
   for (auto& p : c.prof_pending) { cudaEventDestroy(p.beg); cudaEventDestroy(p.end); }
@@ -309,6 +310,12 @@ int titgpu_set_lists(titgpu_ctx* h, int on) {
   return 0;
 }
 unsigned long long titgpu_list_redos(const titgpu_ctx* h) { return h ? h->c.list_redos : 0; }
+int titgpu_set_tiles(titgpu_ctx* h, int on) {
+  if (!h) return 1;
+  h->c.tiles_enabled = on != 0;
+  h->c.tiles_valid = false;
+  return 0;
+}
 int titgpu_set_outputs(titgpu_ctx* h, int level) {
   if (!h) return 1;
   Ctx& c = h->c;
