@@ -163,64 +163,145 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline_sample(dim, budget_s=15.0, n_col=None):
-    """Time the CPU restatement (oracle, -O3 OpenMP build) on a bounded sample of
-    the same workload; returns the cpu_baseline object."""
-    import oracle_lib
+class CpuReference:
+    """The reference's CPU algorithm (oracle/, -O3 OpenMP build, all host cores) timed on the
+    benchmark workload.
 
-    if n_col is None:
-        n_col = 200 if dim == 2 else 28
-    case = make_case(dim, n_col)
-    s = oracle_lib.OracleSolver(dim, fast=True)
-    s.lib.orc_set_num_threads(host_threads())
-    oracle_lib.load_case(s, case)
-    s.initialize()
-    s.step(1)  # warm-up (first-touch, thread pool)
-    steps, t0 = 0, time.perf_counter()
+    2-D workloads run as they are. The 3-D workloads (>= 10 M particles, minutes per step on a
+    CPU) are timed through two bounded samples whose per-phase costs recombine to the workload's
+    own mixture of fluid and wall particles:
+      bulk sample   a wall-free block of fluid at the workload's spacing: seconds per FLUID
+                    particle of every phase (search, pair sums, shifting ...);
+      wall sample   the closed dam-break tank at n_col = 40: what is left of every phase after
+                    the bulk part, per WALL particle (the boundary integrals of compute_gamma and
+                    of the face terms scale with the wetted / meshed wall area).
+    step time of the workload = sum over phases of a_phase n_fluid + b_phase n_fixed. (A single
+    small tank mis-states the mixture: at n_col = 28 it holds 53 % wall particles, C3 15 %.)"""
+
+    PHASES = ("search", "compute_gamma", "setup_boundary", "continuity_momentum", "update_lincomb_dt", "apply_shifts", "free_surface_correction")
+
+    def __init__(self, dim, n_col, tank_z=1.0, bulk=(96, 64, 64), wall_n_col=40):
+        import oracle_lib
+        from titsolver_b200 import cases
+
+        self.dim, self.n_col = dim, n_col
+        self.threads = host_threads()
+
+        def make(case):
+            s = oracle_lib.OracleSolver(dim, fast=True)
+            s.lib.orc_set_num_threads(self.threads)  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+            oracle_lib.load_case(s, case)
+            s.initialize()
+            return s
+
+        if dim == 2:
+            case = cases.dam_break_2d(n_col)
+            self.direct = make(case)
+            self.n_fluid, self.n_fixed = case.n_fluid, case.n_fixed
+            self.sample = f"the workload itself ({case.n} particles)"
+        else:
+            self.direct = None
+            self.n_fluid, self.n_fixed = cases.dam_break_3d_counts(n_col, tank=(5.366, 4.0, tank_z))
+            cb, cw = cases.fluid_block_3d(*bulk, n_col=n_col), cases.dam_break_3d(wall_n_col)
+            self.bulk, self.wall = make(cb), make(cw)
+            self.nb, self.nwf, self.nwx = cb.n_fluid, cw.n_fluid, cw.n_fixed
+            self.sample = (f"per-phase costs of two samples recombined to the workload's {self.n_fluid} fluid + {self.n_fixed} wall particles: a wall-free fluid block "
+                           f"{bulk[0]}x{bulk[1]}x{bulk[2]} ({cb.n_fluid} particles: seconds per fluid particle) and the closed tank at n_col={wall_n_col} "
+                           f"({cw.n_fluid} fluid + {cw.n_fixed} wall particles: the remainder per wall particle)")
+        self.cores = int(oracle_lib.load(True).orc_num_threads())
+        self.phase_s = {k: 0.0 for k in self.PHASES}
+
+    @property
+    def n(self):
+        return self.n_fluid + self.n_fixed
+
+    def step(self):
+        """One SSPRK3 step of the workload: measured (2-D) or recombined from one step of each sample (3-D). Seconds."""
+        if self.direct is not None:
+            self.direct.phase_times()
+            t0 = time.perf_counter()
+            self.direct.step(1)
+            el = time.perf_counter() - t0
+            for k, v in self.direct.phase_times().items():
+                self.phase_s[k] += v
+            return el
+        self.bulk.phase_times(); self.wall.phase_times()
+        self.bulk.step(1); self.wall.step(1)
+        pb, pw = self.bulk.phase_times(), self.wall.phase_times()
+        total = 0.0
+        for k in self.PHASES:
+            a = pb[k] / self.nb
+            b = max(pw[k] - a * self.nwf, 0.0) / self.nwx
+            t = a * self.n_fluid + b * self.n_fixed
+            self.phase_s[k] += t
+            total += t
+        return total
+
+
+def cpu_baseline_sample(dim, n_col, budget_s=30.0, tank_z=1.0):
+    """The cpu_baseline object of the GPU arm's line: `CpuReference` for about `budget_s` seconds."""
+    ref = CpuReference(dim, n_col, tank_z)
+    ref.step()  # warm-up (first touch, thread pool)
+    for k in ref.phase_s:
+        ref.phase_s[k] = 0.0
+    steps, est, t0 = 0, 0.0, time.perf_counter()
     while True:
-        s.step(1)
+        est += ref.step()
         steps += 1
-        el = time.perf_counter() - t0
-        if el >= budget_s or steps >= 50:
+        if time.perf_counter() - t0 >= budget_s or steps >= 20:
             break
-    cores = int(s.lib.orc_num_threads())
-    return {
-        "value": case.n * steps / el, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{steps} SSPRK3 steps of the {dim}D dam break at n_col={n_col} ({case.n} particles, {100.0 * case.n_fixed / case.n:.0f} % of them "
-                  f"wall particles: the closed tank at a size the CPU finishes, so the wall integrals weigh more than at the benchmark size) "
-                  f"in {el:.1f} s, oracle/liboracle_fast.so (-O3, OpenMP, gather form)",
-    }, case.n, steps, el
+    return {"value": ref.n * steps / est, "unit": UNIT, "cores": ref.cores, "kind": "port", "seconds_per_step": est / steps,
+            "phase_seconds_per_step": {k: round(v / steps, 4) for k, v in ref.phase_s.items()},
+            "sample": f"{steps} SSPRK3 steps; {ref.sample}; oracle/liboracle_fast.so (-O3, OpenMP, gather-form pair sums)"}
+
+
+def bench_config(w, args, dim, n_col, world, n_fluid, n_fixed, strong_main):
+    """The `config` object, the same for both arms."""
+    n_job = n_fluid + n_fixed
+    if world == 1:
+        par = "single GPU"
+    elif strong_main:
+        par = f"{world} slabs along x of the fixed tank (strong scaling), one rank per GPU"
+    else:
+        par = f"{world} slabs along z (tank {world}x deeper: weak scaling), one rank per GPU"
+    if world > 1:
+        par += "; inside every step: migration + halo set, 4 ghost refreshes, {N, phi} and shifted-record exchanges (ncclSend/ncclRecv on the context's stream), dt all-reduce"
+    label = w["label"] if not args.n_col else f"{dim}D dam break, n_col={n_col}"
+    if world > 1 and not strong_main:
+        label += f", per GPU; {world} GPUs weak-scaled along z"
+    return {"workload": label, "particles_per_gpu": int(n_job / world), "n_fluid": int(n_fluid), "n_fixed": int(n_fixed),
+            "integrator": "ssprk3", "kernel": "SixthOrderWendland", "eos": "tait", "parallelism": par,
+            "outputs": "value: all 17 fields of all particles published after the last timed step (reference semantics); e2e: state only (r, v, rho) every step",
+            "l2_policy": "inputs larger than L2 (state arrays of %d MB)" % (int(n_job / world) * (2 * dim + 2) * 8 // 2**20)}
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU algorithm alone, on the GPU arm's workload and config."""
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
     dim = w["dim"]
-    # Each "step" is a bounded sample: one SSPRK3 step of the reduced-size case.
-    import oracle_lib
-
-    n_col = args.ref_n_col or (200 if dim == 2 else 28)
-    case = make_case(dim, n_col)
-    s = oracle_lib.OracleSolver(dim, fast=True)
-    s.lib.orc_set_num_threads(host_threads())  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
-    oracle_lib.load_case(s, case)
-    s.initialize()
+    n_col = args.n_col or w["n_col"]
+    strong_main = args.scaling == "strong"
+    tank_z = float(world) if (dim == 3 and world > 1 and not strong_main) else 1.0
+    ref = CpuReference(dim, n_col, tank_z)
     for _ in range(args.warmup):
-        s.step(1)
+        ref.step()
+    for k in ref.phase_s:
+        ref.phase_s[k] = 0.0
     t0 = time.perf_counter()
-    s.step(args.steps)
-    el = time.perf_counter() - t0
-    val = case.n * args.steps / el
-    cores = int(s.lib.orc_num_threads())
-    sample = f"{args.steps} SSPRK3 steps of the {dim}D dam break at n_col={n_col} ({case.n} particles) per run; throughput per particle-update"
+    est = sum(ref.step() for _ in range(args.steps))
+    wall = time.perf_counter() - t0
+    val = ref.n * args.steps / est
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"], "sample_n_col": n_col, "sample_particles": case.n, "integrator": "ssprk3", "kernel": "SixthOrderWendland", "eos": "tait"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "ms_per_step": est / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong_main else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(w, args, dim, n_col, world, ref.n_fluid, ref.n_fixed, strong_main),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": "port", "seconds_per_step": est / args.steps, "measured_wall_seconds": wall,
+                         "phase_seconds_per_step": {k: round(v / args.steps, 4) for k, v in ref.phase_s.items()},
+                         "sample": f"{args.steps} SSPRK3 steps; {ref.sample}; oracle/liboracle_fast.so (-O3, OpenMP, gather-form pair sums)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of the reference (OpenMP); the reference itself (C++26, oneTBB) cannot be built in this image",
+        "note": "CPU restatement of the reference (OpenMP, all host cores); the reference itself (C++26, oneTBB) cannot be built in this image",
     }
     emit(json.dumps(out))
 
@@ -315,15 +396,14 @@ class Runner:
         ms = self.max_over_ranks(ms)
         return ms, clocks, launches, prof
 
-    def rebalance(self, rounds=2, steps=2):
+    def rebalance(self, rounds=2, steps=5):
         """Strong scaling: measure the kernel time per rank over `steps` steps, move the slab edges so
         that every rank carries the same cost, let the next steps migrate the particles; `rounds` times.
         (The end slabs carry the end walls and, the last one, the dry part of the tank.)"""
         if self.slab is None or self.mode != "strong_x":
             return None
         solver, hist = self.solver, []
-        solver.set_outputs(0)
-        for _ in range(rounds):
+        for _ in range(rounds):  # (same call pattern as the timed region: the last step of a call publishes all fields)
             solver.profile(True)
             solver.profile_reset()
             solver.step(steps)
@@ -332,7 +412,6 @@ class Runner:
             edges = self.slab.rebalance(cost, self.extent, max_shift=REBALANCE_SHIFT * self.dr)
             hist.append({"cost_ms": cost, "edges_dr": [round(e / self.dr, 2) for e in edges[1:-1]]})
             solver.step(1)  # migration to the new slabs
-        solver.set_outputs(2)
         return hist
 
     def gather_rank_info(self):
@@ -419,7 +498,7 @@ def run_ours(args, rank, local_rank, world):
     mode = "strong_x" if strong_main else "weak_z"
     run = Runner(args, dim, n_col, rank, local_rank, world, mode)
     solver = run.solver
-    balance = run.rebalance() if not args.no_rebalance else None
+    balance = run.rebalance(steps=args.steps) if not args.no_rebalance else None
     n_job, n_fluid, n_fixed = run.n_total, run.n_fluid, run.n_fixed  # particles of the whole job
     n = n_job / world  # per GPU (wall particles of the halos are not counted twice)
 
@@ -466,7 +545,7 @@ def run_ours(args, rank, local_rank, world):
         sw = WORKLOADS[args.strong_workload]
         srun = Runner(args, 3, args.strong_n_col or sw["n_col"], rank, local_rank, world, "strong_x")
         s_steps = max(2, min(args.steps, 5))
-        s_balance = srun.rebalance() if not args.no_rebalance else None
+        s_balance = srun.rebalance(steps=s_steps) if not args.no_rebalance else None
         s_ms, _, _, s_prof = srun.timed_steps(s_steps, 3, profile=True)
         s_value = srun.n_total * s_steps / (s_ms * 1e-3)
         s_ranks = srun.gather_rank_info()
@@ -485,25 +564,11 @@ def run_ours(args, rank, local_rank, world):
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
-        cpu, _, _, _ = cpu_baseline_sample(dim, args.cpu_budget)
-    if world == 1:
-        par = "single GPU"
-    elif strong_main:
-        par = f"{world} slabs along x of the fixed tank (strong scaling), one rank per GPU"
-    else:
-        par = f"{world} slabs along z (tank {world}x deeper: weak scaling), one rank per GPU"
-    if world > 1:
-        par += "; inside every step: migration + halo set, 4 ghost refreshes, {N, phi} and shifted-record exchanges (ncclSend/ncclRecv on the context's stream), dt all-reduce"
-    label = w["label"] if not args.n_col else f"{dim}D dam break, n_col={n_col}"
-    if world > 1 and not strong_main:
-        label += f", per GPU; {world} GPUs weak-scaled along z"
+        cpu = cpu_baseline_sample(dim, n_col, args.cpu_budget)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong" if strong_main else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": label, "particles_per_gpu": int(n), "n_fluid": int(n_fluid), "n_fixed": int(n_fixed),
-                   "integrator": "ssprk3", "kernel": "SixthOrderWendland", "eos": "tait", "parallelism": par,
-                   "outputs": "value: all 17 fields of all particles published after the last timed step (reference semantics); e2e: state only (r, v, rho) every step",
-                   "l2_policy": "inputs larger than L2 (state arrays of %d MB)" % (int(n) * (2 * dim + 2) * 8 // 2**20)},
+        "config": bench_config(w, args, dim, n_col, world, n_fluid, n_fixed, strong_main),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
@@ -563,8 +628,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--n-col", type=int, default=0, help="override the lattice resolution (parity / debugging runs)")
-    ap.add_argument("--ref-n-col", type=int, default=0, help="sample resolution of the CPU reference arm")
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--cpu-budget", type=float, default=30.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = the workload per GPU (tank N x deeper along z); strong = the workload itself cut into N slabs along x")

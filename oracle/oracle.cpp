@@ -91,6 +91,12 @@ int orc_prepare(void* h) { static_cast<SimBase*>(h)->prepare(); return 0; }
 int orc_rhs_only(void* h) { static_cast<SimBase*>(h)->rhs_only(); return 0; }
 // FluidEquations::post_integrate alone (fluid_equations.hpp:315-321) on the current state.
 int orc_post_only(void* h) { static_cast<SimBase*>(h)->post_only(); return 0; }
+// Seconds per phase since the last call with reset != 0 (see SimBase::phase_s).
+int orc_phase_times(void* h, double* out8, int reset) {
+  auto* s = static_cast<SimBase*>(h);
+  for (int i = 0; i < 8; ++i) { out8[i] = s->phase_s[i]; if (reset) s->phase_s[i] = 0.0; }
+  return 0;
+}
 // Branch counters of the last post_integrate (see SimBase::stats).
 int orc_stats(void* h, long long* out8) { for (int i = 0; i < 8; ++i) out8[i] = static_cast<SimBase*>(h)->stats[i]; return 0; }
 int orc_step(void* h, int nsteps, double* dt_last) {

@@ -24,6 +24,7 @@
 // sums each particle's terms in ascending neighbour index.
 #pragma once
 
+#include <chrono>
 #include <cstdio>
 #include <string>
 
@@ -60,6 +61,17 @@ struct SimBase {
   // [5] shifted with the velocity correction skipped (|gamma - 1| > tiny), [6] free-surface
   // corrections applied (ratio <= 0.99), [7] candidates of the correction (phi != 1).
   long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // Wall-clock seconds per phase, accumulated since the last reset (CPU-baseline breakdown):
+  // [0] search (particle + face adjacency), [1] compute_gamma, [2] setup_boundary,
+  // [3] continuity + momentum (face terms and pair sums), [4] integrator update / lincomb / dt,
+  // [5] apply_shifts, [6] free-surface correction.
+  double phase_s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  struct PhaseTimer {
+    double& acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit PhaseTimer(double& a) : acc(a) {}
+    ~PhaseTimer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  };
   virtual void neighbors(std::vector<std::uint64_t>& off, std::vector<std::uint64_t>& cols) = 0;
   virtual void face_neighbors(std::vector<std::uint64_t>& off, std::vector<std::uint64_t>& cols) = 0;
 };
@@ -330,9 +342,9 @@ struct Sim final : SimBase {
   }
 
   void prepare() override {
-    search();
-    compute_gamma();
-    setup_boundary();
+    { PhaseTimer t(phase_s[0]); search(); }
+    { PhaseTimer t(phase_s[1]); compute_gamma(); }
+    { PhaseTimer t(phase_s[2]); setup_boundary(); }
   }
 
   void initialize() override {
@@ -557,8 +569,8 @@ struct Sim final : SimBase {
   void post_integrate() {
     for (long long& x : stats) x = 0;
     prepare();
-    apply_shifts();
-    apply_free_surface_correction();
+    { PhaseTimer t(phase_s[5]); apply_shifts(); }
+    { PhaseTimer t(phase_s[6]); apply_free_surface_correction(); }
   }
 
   void rhs_only() override {
@@ -570,9 +582,9 @@ struct Sim final : SimBase {
   // ---- time_integrator.hpp ----
   double substep(double dt, bool have_dt) {
     prepare();
-    if (!have_dt) dt = compute_time_step();
-    compute_continuity();
-    compute_momentum();
+    if (!have_dt) { PhaseTimer t(phase_s[4]); dt = compute_time_step(); }
+    { PhaseTimer t(phase_s[3]); compute_continuity(); compute_momentum(); }
+    PhaseTimer t(phase_s[4]);
 #pragma omp parallel for schedule(static)
     for (std::size_t a = 0; a < nf; ++a) {
       r[a] += dt * v[a];
@@ -582,6 +594,7 @@ struct Sim final : SimBase {
     return dt;
   }
   void lincomb(const std::vector<V>& r0, const std::vector<V>& v0, const std::vector<double>& rho0_, double w) {
+    PhaseTimer t(phase_s[4]);
 #pragma omp parallel for schedule(static)
     for (std::size_t a = 0; a < nf; ++a) {
       r[a] = (1 - w) * r0[a] + w * r[a];

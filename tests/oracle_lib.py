@@ -46,6 +46,7 @@ def load(fast: bool = False) -> C.CDLL:
     lib.orc_upload.argtypes = [vp, C.c_char_p, dp]
     lib.orc_download.argtypes = [vp, C.c_char_p, dp]
     lib.orc_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
+    lib.orc_phase_times.argtypes = [vp, dp, C.c_int]
     for f in ("orc_initialize", "orc_prepare", "orc_rhs_only", "orc_post_only"):
         getattr(lib, f).argtypes = [vp]
     lib.orc_step.argtypes = [vp, C.c_int, dp]
@@ -162,6 +163,14 @@ class OracleSolver:
         a = (C.c_longlong * 8)()
         self.lib.orc_stats(self.h, a)
         return dict(zip(self.STAT_NAMES, [int(x) for x in a]))
+
+    PHASE_NAMES = ("search", "compute_gamma", "setup_boundary", "continuity_momentum", "update_lincomb_dt", "apply_shifts", "free_surface_correction")
+
+    def phase_times(self, reset=True):
+        """Seconds per phase accumulated since the last reset (oracle_sim.h, SimBase::phase_s)."""
+        a = (C.c_double * 8)()
+        self.lib.orc_phase_times(self.h, a, int(reset))
+        return dict(zip(self.PHASE_NAMES, [float(x) for x in a]))
 
     def step(self, nsteps=1):
         dt = C.c_double(0)

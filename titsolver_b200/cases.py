@@ -265,6 +265,32 @@ def dam_break_3d(n_col: int = 16, H: float = 0.6, wall_ratio: float = 1.0, tank=
                 {"name": f"dam_break_3d_{WM}x{WN}x{WK}", "tank": ext, "wall_ratio": wall_ratio, "jitter": jitter})
 
 
+def dam_break_3d_counts(n_col: int, tank=(5.366, 4.0, 1.0)):
+    """(n_fluid, n_fixed) of `dam_break_3d(n_col, tank=tank)` without building it."""
+    ncell = tuple(max(1, int(math.ceil(t * n_col - 1e-9))) for t in tank)
+    n_fixed = int(np.prod([c + 1 for c in ncell]) - np.prod([c - 1 for c in ncell]))
+    return 2 * n_col * n_col * (int(round(tank[2] * n_col)) - 1), n_fixed
+
+
+def fluid_block_3d(nx: int, ny: int, nz: int, H: float = 0.6, n_col: int = 171) -> Case:
+    """A block of nx x ny x nz fluid particles at the spacing of `dam_break_3d(n_col)` with no
+    walls at all (gamma = 1 everywhere): the bulk part of the dam break, for timing the
+    per-fluid-particle cost of a CPU implementation apart from its wall integrals."""
+    dr = H / float(n_col)
+    g, rho0 = 9.81, 1000.0
+    cs0 = 20 * math.sqrt(g * H)
+    ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    rf = dr * np.stack([ii.ravel() + 1.0, jj.ravel() + 1.0, kk.ravel() + 1.0], axis=1)
+    nf = rf.shape[0]
+    big = 10.0 * dr * max(nx, ny, nz) + 1.0
+    cverts, cfaces = _box_wall_mesh((2 * big,) * 3, (1, 1, 1), inward=False)
+    cverts = cverts - big
+    rho = rho0 + rho0 * g * (dr * ny - rf[:, 1]) / cs0**2
+    e = np.zeros((0, 3))
+    return Case(3, nf, 0, rf, np.full(nf, rho0 * dr**3), rho, e, e.astype(np.uint64), cverts, cfaces, g, 0.001, cs0, rho0, 7.0, 2.0 * dr, dr, H,
+                {"name": f"fluid_block_3d_{nx}x{ny}x{nz}", "tank": (2 * big,) * 3})
+
+
 def tetra_tank_3d(n_side: int = 10, L: float = 1.0, wall_ratio: float = 0.93, jitter: float = 0.1, seed: int = 7, fill: float = 0.55) -> Case:
     """Fluid in a tetrahedral tank (0,0,0), (L,0,0), (0,L,0), (0,0,L): a wall surface
     with slanted, red-refined triangles (`tessellate_3d`, the reference's 3-D set-up
