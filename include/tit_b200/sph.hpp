@@ -464,7 +464,8 @@ public:
   /// Write all varying fields as one frame of `series` (particle_array.hpp:165-172):
   /// one array per field, named after the field, in the field-set order. Needs
   /// `publish(Publish::all)` during the step before (the default).
-  void write(Real time, data::SeriesView<data::Storage> series) {
+  void write(Real time, data::SeriesView<data::Storage> series) const {
+    if (publish_ != Publish::all && stepped_) throw Exception("ParticleArray::write: the last step did not publish every field (publish(Publish::all) before it)");
     const auto frame = series.create_frame(static_cast<float64_t>(time));
     for (int f = 0; f < num_varying_fields; ++f) {
       fetch_(f);
@@ -512,6 +513,19 @@ public:
     }
   }
 
+  /// Read-only `field[particles]` (const array): fetches the device copy if it is newer and does NOT
+  /// mark the host copy as written - `std::as_const(particles)[r]` between steps costs no re-upload.
+  template<int Id, tit::impl::Rank R>
+  auto operator[](tit::impl::Field<Id, R> /*field*/) const -> decltype(auto) {
+    if constexpr (Id < 0) { return static_cast<const Real&>(h_); }
+    else {
+      fetch_(Id);
+      if constexpr (R == tit::impl::Rank::scalar) return std::span<const Real>{cols_[Id]};
+      else if constexpr (R == tit::impl::Rank::vector) return std::span<const V>{reinterpret_cast<const V*>(cols_[Id].data()), size()};
+      else return std::span<const M>{reinterpret_cast<const M*>(cols_[Id].data()), size()};
+    }
+  }
+
   /// Which derived fields a step publishes (default: everything, as the reference).
   void publish(Publish level) { publish_ = level; if (ctx_raw_ != nullptr) call_(titgpu_set_outputs(ctx_raw_, static_cast<int>(level)), "titgpu_set_outputs"); }
 
@@ -552,7 +566,7 @@ public:
     }
     return ctx_raw_;
   }
-  void call_(int rc, const char* what) {
+  void call_(int rc, const char* what) const {
     if (rc != 0) throw Exception(std::string(what) + ": " + titgpu_last_error(ctx_raw_));
   }
   void require_integrator_(int id) {
@@ -560,7 +574,9 @@ public:
   }
   template<class Equations, class Mesh>
   void bind_(const Equations& eq, const Mesh& mesh) {
-    if (bound_ == static_cast<const void*>(&eq) && !params_dirty_) return;
+    // (a mere READ of h through the non-const accessor sets params_dirty_: rebind - which rebuilds the
+    // search grid and the wall cache - only if the value really changed)
+    if (bound_ == static_cast<const void*>(&eq) && (!params_dirty_ || h_ == bound_h_)) { params_dirty_ = false; return; }
     using Eq = std::remove_cvref_t<Equations>;
     static_assert(Eq::dim == Dim);
     if (Eq::kernel_id != kernel_id_ || Eq::eos_id != eos_id_) throw Exception("the particle array was built for other equations");
@@ -578,6 +594,7 @@ public:
                              eq.containment().num_faces()),
           "titgpu_set_surface");
     bound_ = &eq;
+    bound_h_ = h_;
     params_dirty_ = false;
   }
   /// Upload the host-written input fields (state + the dv_dt seed of the time-step limit).
@@ -591,7 +608,7 @@ public:
     }
     resized_ = false;
   }
-  void mark_device_newer_() { device_newer_.fill(true); }
+  void mark_device_newer_() { device_newer_.fill(true); stepped_ = true; }
 
   template<int Id, tit::impl::Rank R>
   auto at_(std::size_t index, tit::impl::Field<Id, R> /*field*/) -> decltype(auto) {
@@ -617,7 +634,7 @@ private:
     host_dirty_[f] = true;
   }
   /// Read-only host access: fetch the device copy if it is newer.
-  void fetch_(int f) {
+  void fetch_(int f) const {
     if (!device_newer_[f]) return;
     device_newer_[f] = false;
     if (ctx_raw_ != nullptr && size() > 0) call_(titgpu_download(ctx_raw_, varying_field_names[f], cols_[f].data(), 0), "titgpu_download");
@@ -627,12 +644,16 @@ private:
   int kernel_id_, eos_id_, integrator_id_, device_;
   titgpu_ctx* ctx_raw_ = nullptr;
   const void* bound_ = nullptr;
-  bool params_dirty_ = true, resized_ = true;
+  Real bound_h_{};
+  mutable bool params_dirty_ = true;
+  bool resized_ = true;
   Publish publish_ = Publish::all;
   Real h_{};
   std::array<std::size_t, 3> ranges_{0, 0, 0};
-  std::array<std::vector<Real>, num_varying_fields> cols_;
-  std::array<bool, num_varying_fields> host_dirty_{}, device_newer_{};
+  mutable std::array<std::vector<Real>, num_varying_fields> cols_;  // (mutable: a const read may fetch the device copy)
+  std::array<bool, num_varying_fields> host_dirty_{};
+  mutable std::array<bool, num_varying_fields> device_newer_{};
+  bool stepped_ = false;
 };
 template<class Real, std::size_t Dim, class Integrator>
 ParticleArray(Space<Real, Dim>, const Integrator&) -> ParticleArray<Real, Dim>;
