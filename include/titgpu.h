@@ -116,6 +116,15 @@ TITGPU_API int titgpu_set_outputs(titgpu_ctx* ctx, int level);
 TITGPU_API int titgpu_set_lists(titgpu_ctx* ctx, int on);
 TITGPU_API unsigned long long titgpu_list_redos(const titgpu_ctx* ctx);
 
+/* Whole steps as CUDA graphs (default ON; 2-D contexts without a slab decomposition, candidate
+ * lists or profiling). The 2-D step has no host read-back, so its ~65 launches are recorded once
+ * per state of the ping-pong buffers (they return to the same roles every third SSPRK step) and
+ * replayed with one cudaGraphLaunch: the reference's default case (14 300 particles) is bound by
+ * launch latency, not by any kernel. Results are bit-identical with graphs on or off.
+ * TITGPU_GRAPHS=0 in the environment or titgpu_set_graphs(ctx, 0) turns them off. */
+TITGPU_API int titgpu_set_graphs(titgpu_ctx* ctx, int on);
+TITGPU_API unsigned long long titgpu_graph_replays(const titgpu_ctx* ctx);
+
 /* Shared-memory-staged kernel-sum pass (3-D, kernels of support radius 2h; default OFF;
  * titgpu_set_tiles(ctx, 1) or the environment TITGPU_TILES=1 turns it on): one block per tile of
  * 2 x 2 x 2 search cells stages the 36 contiguous record runs of the 6 x 6 x 6 cells around it

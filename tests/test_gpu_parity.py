@@ -377,3 +377,30 @@ def test_errors_are_reported():
     s = tb.Solver(2)
     with pytest.raises(tb.TitGpuError):
         s.step(1)  # nothing set up yet
+
+
+def test_cuda_graph_replay_is_bit_identical_2d():
+    """titgpu_set_graphs: whole 2-D steps recorded once per ping-pong state (period three) and
+    replayed; nothing about the results may change, whatever the mix of step() calls, output
+    levels and uploads in between."""
+    case = cases.dam_break_2d(24)
+    res = []
+    for graphs in (True, False):
+        g = tb.Solver(2)
+        g.set_graphs(graphs)
+        tb.load_case(g, case)
+        g.initialize()
+        g.step(1)
+        g.step(7)
+        g.set_outputs(1)
+        g.step(2)
+        r = g.download("r")
+        g.upload("r", r)  # an upload that moves nothing keeps the graphs valid
+        g.set_outputs(2)
+        g.step(4)
+        res.append({f: g.download(f) for f in STEP_FIELDS + ("N", "phi", "dv_dt", "p")})
+        res[-1]["launches"] = g.launch_count
+        assert (g.graph_replays > 0) == graphs
+    for f in STEP_FIELDS + ("N", "phi", "dv_dt", "p"):
+        assert np.array_equal(res[0][f], res[1][f]), f
+    assert res[0]["launches"] == res[1]["launches"]  # replayed launches are counted too

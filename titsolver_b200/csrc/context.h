@@ -117,6 +117,24 @@ struct Ctx {
   DBuf tile_list, tile_count;                      // tile ids | {count, work cursor}
   int tile_nty = 0, tile_ntz = 0;
 
+  // CUDA graphs of whole steps (2-D: the step has no host read-back). One graph per state of
+  // the ping-pong buffers (they return to the same roles every third SSPRK step) and output
+  // flag; dropped whenever the particle set, the grid or the parameters change.
+  struct StepGraph {
+    void* key[10];   // A, A_alt, A0, A0_alt, B, B_alt, B0, B0_alt, orig, orig_alt before the step
+    void* after[10]; // ... and after it
+    int write_out, output_level;
+    unsigned long long launches;
+    cudaGraphExec_t exec;
+  };
+  bool graphs_enabled = true;  // TITGPU_GRAPHS=0 / titgpu_set_graphs
+  std::vector<StepGraph> graphs;
+  unsigned long long graph_replays = 0;
+  void drop_graphs() {
+    for (StepGraph& g : graphs) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+  }
+
   // Hash / sort scratch.
   DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp, cell_fs, cell_fluid;
 

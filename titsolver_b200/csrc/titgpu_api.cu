@@ -76,6 +76,7 @@ int alloc_particles(Ctx& c) {
   c.sorted_identity = true;
   c.grid_ready = false;
   c.fixed_cache_valid = false;
+  c.drop_graphs();
   c.sized = true;
   c.prm.nf = int(c.nf); c.prm.nx = int(c.nx); c.prm.n = int(c.n); c.prm.n_owned = int(c.nf);
   return 0;
@@ -126,6 +127,7 @@ int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_
   c.prm.eos = eos_id;
   if (const char* e = std::getenv("TITGPU_LISTS")) c.lists_enabled = e[0] != '0';
   if (const char* e = std::getenv("TITGPU_TILES")) c.tiles_enabled = e[0] != '0';
+  if (const char* e = std::getenv("TITGPU_GRAPHS")) c.graphs_enabled = e[0] != '0';
   return 0;
 }
 
@@ -143,6 +145,7 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
   for (auto& p : c.prof_pending) { cudaEventDestroy(p.beg); cudaEventDestroy(p.end); }
   for (DBuf& b : c.out) b.release();
+  c.drop_graphs();
   delete c.mg.tr;
   c.mg.tr = nullptr;
   for (DBuf* b : {&c.mg.sendA, &c.mg.sendB, &c.mg.recvA, &c.mg.recvB, &c.mg.send_idx, &c.mg.migA[0], &c.mg.migA[1], &c.mg.migB[0], &c.mg.migB[1], &c.mg.migG[0], &c.mg.migG[1], &c.mg.gid,
@@ -310,6 +313,13 @@ int titgpu_set_lists(titgpu_ctx* h, int on) {
   return 0;
 }
 unsigned long long titgpu_list_redos(const titgpu_ctx* h) { return h ? h->c.list_redos : 0; }
+int titgpu_set_graphs(titgpu_ctx* h, int on) {
+  if (!h) return 1;
+  h->c.graphs_enabled = on != 0;
+  if (!on) h->c.drop_graphs();
+  return 0;
+}
+unsigned long long titgpu_graph_replays(const titgpu_ctx* h) { return h ? h->c.graph_replays : 0; }
 int titgpu_set_tiles(titgpu_ctx* h, int on) {
   if (!h) return 1;
   h->c.tiles_enabled = on != 0;
