@@ -177,6 +177,12 @@ TITGPU_API int titgpu_mg_reserve(titgpu_ctx* ctx, size_t max_fluid);
  * pass of the step). `fluid_total` >= 0 makes every step verify that the ranks together
  * still own that many fluid particles. An interior slab thinner than `halo` is refused. */
 TITGPU_API int titgpu_mg_set_slab(titgpu_ctx* ctx, int axis, double lo, double hi, double halo, long long fluid_total);
+/* Optional: away from the walls a neighbouring slab reads nothing beyond ONE support radius of its
+ * own particles; the full `halo` is only needed for the fluid that can lie within a support radius
+ * of a wall particle (the wall density is extrapolated from it, fluid_equations.hpp:122-164). With
+ * `halo_pair` = support radius + margin (< halo) the ghost layer is that thin everywhere except along
+ * the walls - about half the ghosts and half the bytes per exchange. 0 (default) = `halo` everywhere. */
+TITGPU_API int titgpu_mg_set_halo_pair(titgpu_ctx* ctx, double halo_pair);
 /* Global ids of the fluid particles uploaded so far (they travel with the particles). */
 TITGPU_API int titgpu_mg_set_gids(titgpu_ctx* ctx, const int64_t* gids);
 /* Communicator. Either adopt the host's ncclComm_t (rank r talks to r - 1 and r + 1), or

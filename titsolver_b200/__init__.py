@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
     "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_set_tiles", "titgpu_set_graphs", "titgpu_graph_replays", "titgpu_mg_reserve", "titgpu_mg_counts",
-    "titgpu_mg_set_slab", "titgpu_mg_set_gids", "titgpu_mg_attach_comm", "titgpu_mg_nccl_unique_id", "titgpu_mg_attach_nccl", "titgpu_mg_hub_create", "titgpu_mg_hub_destroy",
+    "titgpu_mg_set_slab", "titgpu_mg_set_halo_pair", "titgpu_mg_set_gids", "titgpu_mg_attach_comm", "titgpu_mg_nccl_unique_id", "titgpu_mg_attach_nccl", "titgpu_mg_hub_create", "titgpu_mg_hub_destroy",
     "titgpu_mg_attach_hub", "titgpu_mg_detach", "titgpu_mg_download_owned", "titgpu_mg_upload_owned", "titgpu_mg_stats",
     "titgpu_neighbors", "titgpu_face_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
     "titgpu_profile_enable", "titgpu_profile_reset", "titgpu_profile_count", "titgpu_profile_get", "titgpu_measure_fp64_peak",
@@ -79,6 +79,7 @@ def load_library() -> C.CDLL:
     lib.titgpu_mg_reserve.argtypes = [vp, sz]
     lib.titgpu_mg_counts.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
     lib.titgpu_mg_set_slab.argtypes = [vp, C.c_int, d, d, d, C.c_longlong]
+    lib.titgpu_mg_set_halo_pair.argtypes = [vp, d]
     lib.titgpu_mg_set_gids.argtypes = [vp, vp]
     lib.titgpu_mg_attach_comm.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.titgpu_mg_nccl_unique_id.argtypes = [vp]
@@ -250,6 +251,9 @@ class Solver:
 
     def mg_set_slab(self, axis, lo, hi, halo, fluid_total=-1):
         self._ck(self.lib.titgpu_mg_set_slab(self.h, int(axis), float(lo), float(hi), float(halo), int(fluid_total)), "titgpu_mg_set_slab")
+
+    def mg_set_halo_pair(self, halo_pair):
+        self._ck(self.lib.titgpu_mg_set_halo_pair(self.h, float(halo_pair)), "titgpu_mg_set_halo_pair")
 
     def mg_set_gids(self, gids):
         g = _arr(gids, np.int64)

@@ -181,6 +181,7 @@ struct Params {
   double w_val;   // weight<D> h^-D
   double w_flux;  // weight<D> h^-1
   double w_anti;  // weight<D>
+  double inv_rho0, tait_b;  // 1 / rho0 and rho0 cs0^2 / xi: loop invariants of the pair passes, read from the constant bank
   double k_fs;    // -log(0.05) / 0.01^2
   double cos_fov2;  // cos(pi/4)^2 as evaluated in double (fluid_equations.hpp:406-407)
   int eos;

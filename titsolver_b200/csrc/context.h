@@ -57,6 +57,7 @@ struct MgState {
   int axis = 0;
   double lo = -HUGE_VAL, hi = HUGE_VAL;  // owned slab [lo, hi) along `axis`
   double halo = 0;                       // ghost-layer width (incl. the margin for the motion within a step)
+  double halo_pair = 0;                  // ... of which away from the walls only this much is needed (0 = all of it)
   int left = -1, right = -1;             // neighbour ranks (-1 = none)
   // The halo set of the current step: n_send[s] owned particles go to side s (0 left, 1 right),
   // n_recv[s] ghosts come from it. Buffers hold [left part | right part].
@@ -139,7 +140,7 @@ struct Ctx {
   DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp, cell_fs, cell_fluid;
 
   // Static boundary.
-  DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin, fterm, favg;
+  DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin, fterm, fgeom, favg;
   // 3-D wall pipeline work lists (engine.cuh, k_wsearch) and their capacities in entries.
   DBuf ww_faces, ww_sref, ww_items, ww_val, ww_rims, ww_val2, ww_act, ww_ovf, ww_x2, ww_cur, ww_list;
   size_t ww_cap_faces = 0, ww_cap_items = 0, ww_cap_rims = 0, ww_cap_act = 0;

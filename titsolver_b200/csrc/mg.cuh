@@ -65,17 +65,33 @@ static __global__ void k_mg_scatter_owned(const double4* __restrict__ A, const d
   else { const int k = s_r[o]; mA_r[k] = ra; mB_r[k] = rb; mg_r[k] = g; }
 }
 
-// Which owned particles (canonical order, after the migration) lie within `halo` of a
-// neighbouring slab. A particle outside its owner's slab at this point crossed more than
-// one slab within a step: flagged, the host reports it.
+// Which owned particles (canonical order, after the migration) the neighbouring slab needs as
+// ghosts: everything within `halo_pair` of it (the neighbours of its own particles: one support
+// radius + margin), and up to `halo` (two radii + the wall-face edge + margin) the particles that
+// can lie within a support radius of a WALL particle - the neighbour extrapolates the density of
+// its wall particles from them (fluid_equations.hpp:122-164); away from the walls nothing beyond
+// one radius is ever read. (fflag / CF_WALL: a boundary face within reach of the particle's
+// face-grid cell.) A particle outside its owner's slab at this point crossed more than one slab
+// within a step: flagged, the host reports it.
 template<int D>
-__global__ void k_mg_band(const double4* __restrict__ A, int n_owned, int axis, double lo, double hi, double halo, int has_l, int has_r, int* __restrict__ in_l, int* __restrict__ in_r,
-                          int* __restrict__ bad) {
+__global__ void k_mg_band(const double4* __restrict__ A, int n_owned, int axis, double lo, double hi, double halo_pair, double halo, GridDesc fg, const unsigned char* __restrict__ fflag, int has_l,
+                          int has_r, int* __restrict__ in_l, int* __restrict__ in_r, int* __restrict__ bad) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_owned) return;
-  const double x = mg_axis_coord<D>(A[o], axis);
-  in_l[o] = has_l && x < lo + halo;
-  in_r[o] = has_r && x >= hi - halo;
+  const double4 a = A[o];
+  const double x = mg_axis_coord<D>(a, axis);
+  const bool l2 = has_l && x < lo + halo, r2 = has_r && x >= hi - halo;
+  bool near_wall = true;
+  if ((l2 && !(x < lo + halo_pair)) || (r2 && !(x >= hi - halo_pair))) {
+    Vec<D> r;
+    r[0] = a.x; r[1] = a.y;
+    if constexpr (D == 3) r[2] = a.z;
+    int fci[D];
+    cell_coords<D>(fg, r, fci);
+    near_wall = (fflag[cell_flat<D>(fg, fci)] & CF_WALL) != 0;
+  }
+  in_l[o] = l2 && (x < lo + halo_pair || near_wall);
+  in_r[o] = r2 && (x >= hi - halo_pair || near_wall);
   if ((has_l && x < lo) || (has_r && x >= hi)) *bad = 1;
 }
 

@@ -339,11 +339,21 @@ TIT_HD int triangle_degeneracy(const Vec<3>& a, const Vec<3>& b, const Vec<3>& c
   if (bc >= ca2) return 2;
   return 3;
 }
-TIT_HD bool face_intersects(const FaceFrame<3>& f, const Vec<3>& p, double radius, double radius2, double tiny) {
-  for (int d = 0; d < 3; ++d)
-    if (!(p[d] - radius <= f.hi[d] && f.lo[d] <= p[d] + radius)) return false;
+// The 80 bytes of a triangle the exact test reads (the face search gathers these per candidate
+// face; the ~350-byte frame is only needed by the edge integrals).
+struct FaceGeom3 {
+  double a[3], b[3], c[3];
+  int degen, pad;
+};
+static_assert(sizeof(FaceGeom3) == 80, "FaceGeom3 must stay 80 bytes");
+template<class F3>  // FaceFrame<3> or FaceGeom3
+TIT_HD bool face_intersects3(const F3& f, const Vec<3>& p, double radius, double radius2, double tiny) {
   Vec<3> a, b, c, q;
   for (int d = 0; d < 3; ++d) { a[d] = f.a[d]; b[d] = f.b[d]; c[d] = f.c[d]; }
+  for (int d = 0; d < 3; ++d) {  // bbox of the triangle (geom/triangle.hpp box(): min / max of the vertices)
+    const double lo = fmin(fmin(a[d], b[d]), c[d]), hi = fmax(fmax(a[d], b[d]), c[d]);
+    if (!(p[d] - radius <= hi && lo <= p[d] + radius)) return false;
+  }
   if (f.degen) {
     q = f.degen == 1 ? clamp_to_segment<3>(a, b, p, tiny) : f.degen == 2 ? clamp_to_segment<3>(b, c, p, tiny) : clamp_to_segment<3>(a, c, p, tiny);
   } else {
@@ -380,5 +390,6 @@ TIT_HD bool face_intersects(const FaceFrame<3>& f, const Vec<3>& p, double radiu
   const Vec<3> x = xsubv(q, p);
   return xdot(x, x) <= radius2;
 }
+TIT_HD bool face_intersects(const FaceFrame<3>& f, const Vec<3>& p, double radius, double radius2, double tiny) { return face_intersects3(f, p, radius, radius2, tiny); }
 
 }  // namespace titgpu

@@ -259,7 +259,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_rhs_tile(Dev<3> S, RhsArgs 
   __syncthreads();
   unsigned phase = 0;
   const int n_tiles = *n_tiles_ptr;
-  const double wh = P.w_val * P.hinv;
   double f2max = 0.0;
   unsigned short* list = T.list[warp];
   // Tiles are dealt round-robin (a block's tiles are spread over the whole list, so the fluid-full
@@ -363,7 +362,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_rhs_tile(Dev<3> S, RhsArgs 
           PState<D> sb;
           sb.r[0] = hf ? a1.x : a0.x; sb.r[1] = hf ? a1.y : a0.y; sb.r[2] = hf ? a0.x : a1.x; sb.rho = hf ? a0.y : a1.y;
           sb.v[0] = hf ? b1_.x : b0_.x; sb.v[1] = hf ? b1_.y : b0_.y; sb.v[2] = hf ? b0_.x : b1_.x; sb.m = hf ? b0_.y : b1_.y;
-          rhs_pair<D, KID, EOSK>(P, wh, ra, va, rho_a, cs_a, Pa, K_a, sb, make_double4(0.0, 0.0, 0.0, 0.0), act, pc, pm);
+          rhs_pair<D, KID, EOSK>(P, ra, va, rho_a, cs_a, Pa, K_a, sb, make_double4(0.0, 0.0, 0.0, 0.0), act, pc, pm);
         }
         pc = warp_sum(pc);
         pm = warp_sum(pm);

@@ -139,7 +139,7 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (DBuf& b : c.bufB) b.release();
   for (DBuf& b : c.buf_orig) b.release();
   for (DBuf* b : {&c.C, &c.F, &c.gamma_w, &c.gg_w, &c.wsum, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.fs_flag, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm,
-                  &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.cell_fs, &c.cell_fluid, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.ftwin, &c.fterm, &c.favg, &c.ww_faces, &c.ww_sref, &c.ww_items, &c.ww_val, &c.ww_rims, &c.ww_val2, &c.ww_act, &c.ww_ovf, &c.ww_x2, &c.ww_cur, &c.ww_list, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
+                  &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.cell_fs, &c.cell_fluid, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.ftwin, &c.fterm, &c.fgeom, &c.favg, &c.ww_faces, &c.ww_sref, &c.ww_items, &c.ww_val, &c.ww_rims, &c.ww_val2, &c.ww_act, &c.ww_ovf, &c.ww_x2, &c.ww_cur, &c.ww_list, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
                   &c.rho_fx, &c.p_fx, &c.staging, &c.scalars, &c.tile_list, &c.tile_count, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
     b->release();
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
@@ -347,6 +347,14 @@ int titgpu_mg_counts(titgpu_ctx* h, size_t* n_owned, size_t* n_ghost, size_t* n_
   if (n_owned) *n_owned = size_t(c.prm.n_owned);
   if (n_ghost) *n_ghost = c.nf - size_t(c.prm.n_owned);
   if (n_fixed) *n_fixed = c.nx;
+  return 0;
+}
+int titgpu_mg_set_halo_pair(titgpu_ctx* h, double halo_pair) {
+  if (!h) return 1;
+  Ctx& c = h->c;
+  if (!(halo_pair >= 0)) return fail(c, "titgpu_mg_set_halo_pair: negative width");
+  c.mg.halo_pair = halo_pair;
+  c.mg.set_valid = false;
   return 0;
 }
 int titgpu_mg_set_slab(titgpu_ctx* h, int axis, double lo, double hi, double halo, long long fluid_total) {

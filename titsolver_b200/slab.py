@@ -250,7 +250,7 @@ class SlabSolver:
     MARGIN_DR = 1.0  # extra halo, in particle spacings, for the motion within one step
 
     def __init__(self, case, rank, world, axis=0, edges=None, device=0, kernel_id=4, eos_id=0, integrator_id=3, group=None, reserve=None, local=False, hub=None,
-                 fluid_total=None):
+                 fluid_total=None, thin_halo=True):
         """`case` is the GLOBAL case (every rank cuts out its slab; small runs and
         tests) or, with `local=True`, the rank-local one made by
         `cases.dam_break_3d_slab` (`edges` required, `case.meta["gid"]` = global ids)."""
@@ -300,6 +300,8 @@ class SlabSolver:
         s.mg_set_gids(gid)
         self.fluid_total = fluid_total
         s.mg_set_slab(axis, lo, hi, halo, fluid_total)
+        if thin_halo:  # one support radius + margin away from the walls, the full halo along them
+            s.mg_set_halo_pair(R + self.MARGIN_DR * case.dr)
         if world > 1:
             if hub is not None:
                 s.mg_attach_hub(hub, rank)
