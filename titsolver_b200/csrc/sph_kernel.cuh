@@ -36,9 +36,7 @@ template<> struct FaceFrame<3> {
   double et[3][2], elen[3];  // unit tangent and length of the edges a->b, b->c, c->a in the (e1, e2) frame
   double ctr[3];
   double lo[3], hi[3];
-  double b[3], c[3];    // second / third vertex in world coordinates (the exact intersection test)
   unsigned v[3];
-  int degen;            // triangle_degeneracy(): the reference clamps a near-zero-area triangle to its longest edge
 };
 
 template<int KID>
@@ -346,8 +344,7 @@ struct FaceGeom3 {
   int degen, pad;
 };
 static_assert(sizeof(FaceGeom3) == 80, "FaceGeom3 must stay 80 bytes");
-template<class F3>  // FaceFrame<3> or FaceGeom3
-TIT_HD bool face_intersects3(const F3& f, const Vec<3>& p, double radius, double radius2, double tiny) {
+TIT_HD bool face_intersects3(const FaceGeom3& f, const Vec<3>& p, double radius, double radius2, double tiny) {
   Vec<3> a, b, c, q;
   for (int d = 0; d < 3; ++d) { a[d] = f.a[d]; b[d] = f.b[d]; c[d] = f.c[d]; }
   for (int d = 0; d < 3; ++d) {  // bbox of the triangle (geom/triangle.hpp box(): min / max of the vertices)
@@ -390,6 +387,4 @@ TIT_HD bool face_intersects3(const F3& f, const Vec<3>& p, double radius, double
   const Vec<3> x = xsubv(q, p);
   return xdot(x, x) <= radius2;
 }
-TIT_HD bool face_intersects(const FaceFrame<3>& f, const Vec<3>& p, double radius, double radius2, double tiny) { return face_intersects3(f, p, radius, radius2, tiny); }
-
 }  // namespace titgpu
