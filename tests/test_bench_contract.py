@@ -21,7 +21,25 @@ def test_ncu_traffic_comes_from_the_committed_capture():
     t, src = bench.ncu_traffic(3, 1000)
     assert t is not None and t > 128 * 1000  # DRAM traffic is above the algorithmic bytes
     assert "profiles/" in src and os.path.exists(os.path.join(ROOT, src.split(":")[0]))
-    assert bench.ncu_traffic(2, 1000) == (None, None)
+    t2, src2 = bench.ncu_traffic(2, 1000)
+    assert t2 > 96 * 1000 and os.path.exists(os.path.join(ROOT, src2.split(":")[0]))
+    pipes = bench.ncu_pipes(3)
+    assert 0 < pipes["fp64_pct"] < 100 and 0 < pipes["fma_fp32_pct"] < 100 and 0 < pipes["issue_slots_pct"] <= 100
+
+
+def test_both_arms_share_one_config():
+    """`same_config`: the reference arm describes the workload with the GPU arm's own function."""
+    import argparse
+
+    args = argparse.Namespace(n_col=0)
+    w = bench.WORKLOADS["c3"]
+    from titsolver_b200 import cases
+
+    nf, nx = cases.dam_break_3d_counts(w["n_col"])
+    cfg = bench.bench_config(w, args, 3, w["n_col"], 1, nf, nx, False)
+    assert cfg["workload"] == w["label"] and cfg["n_fluid"] == 9941940 and cfg["n_fixed"] == 1803710 and cfg["particles_per_gpu"] == nf + nx
+    cfg8 = bench.bench_config(w, args, 3, w["n_col"], 8, *cases.dam_break_3d_counts(w["n_col"], (5.366, 4.0, 8.0)), False)
+    assert "8 GPUs weak-scaled" in cfg8["workload"] and cfg8["n_fluid"] == 79944894
 
 
 def test_reference_arm_prints_one_json_line():

@@ -150,6 +150,10 @@ struct Ctx {
   DBuf gamma_fixed, gg_fixed;  // static gamma / grad gamma of the fixed particles
   DBuf rho_fx, p_fx;           // wall density / pressure by fixed id
   bool fixed_cache_valid = false;
+  // Published fields of wall particles far from any fluid are static (engine.cuh, k_deep_dry).
+  double wall_edge_max = 0;  // longest bounding-box diagonal of a wall face (setup_grid)
+  DBuf dry_pub, dry_skip;
+  bool dry_pub_valid = false, dry_cache_enabled = true;  // TITGPU_DRY_CACHE=0 recomputes them at every publishing step
 
   // Outputs, original particle order, one buffer per field.
   DBuf out[F_COUNT];

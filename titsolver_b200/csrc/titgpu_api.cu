@@ -77,6 +77,7 @@ int alloc_particles(Ctx& c) {
   c.grid_ready = false;
   c.fixed_cache_valid = false;
   c.drop_graphs();
+  c.dry_pub_valid = false;
   c.sized = true;
   c.prm.nf = int(c.nf); c.prm.nx = int(c.nx); c.prm.n = int(c.n); c.prm.n_owned = int(c.nf);
   return 0;
@@ -128,6 +129,7 @@ int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_
   if (const char* e = std::getenv("TITGPU_LISTS")) c.lists_enabled = e[0] != '0';
   if (const char* e = std::getenv("TITGPU_TILES")) c.tiles_enabled = e[0] != '0';
   if (const char* e = std::getenv("TITGPU_GRAPHS")) c.graphs_enabled = e[0] != '0';
+  if (const char* e = std::getenv("TITGPU_DRY_CACHE")) c.dry_cache_enabled = e[0] != '0';
   return 0;
 }
 
@@ -140,7 +142,7 @@ int titgpu_destroy(titgpu_ctx* h) {
   for (DBuf& b : c.buf_orig) b.release();
   for (DBuf* b : {&c.C, &c.F, &c.gamma_w, &c.gg_w, &c.wsum, &c.gamma_s, &c.N_s, &c.phi_s, &c.phi2_s, &c.dr_s, &c.gv_s, &c.gr_s, &c.fs_flag, &c.cell_id, &c.slot, &c.tmp_perm, &c.perm,
                   &c.cell_cnt, &c.cell_start, &c.cub_tmp, &c.cell_fs, &c.cell_fluid, &c.frames, &c.fcell_start, &c.fcell_faces, &c.face_cells, &c.fflag, &c.ftwin, &c.fterm, &c.fgeom, &c.favg, &c.ww_faces, &c.ww_sref, &c.ww_items, &c.ww_val, &c.ww_rims, &c.ww_val2, &c.ww_act, &c.ww_ovf, &c.ww_x2, &c.ww_cur, &c.ww_list, &c.cverts, &c.cfaces, &c.gamma_fixed, &c.gg_fixed,
-                  &c.rho_fx, &c.p_fx, &c.staging, &c.scalars, &c.tile_list, &c.tile_count, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
+                  &c.rho_fx, &c.p_fx, &c.dry_pub, &c.dry_skip, &c.staging, &c.scalars, &c.tile_list, &c.tile_count, &c.nl_idx, &c.nl_cnt, &c.bakA, &c.bakB, &c.bak_orig})
     b->release();
   for (cudaEvent_t e : c.prof_pool) cudaEventDestroy(e);
   for (auto& p : c.prof_pending) { cudaEventDestroy(p.beg); cudaEventDestroy(p.end); }
@@ -172,6 +174,7 @@ int titgpu_set_params(titgpu_ctx* h, double g, double mu, double cs0, double rho
   c.params_set = true;
   c.grid_ready = false;
   c.fixed_cache_valid = false;
+  c.dry_pub_valid = false;
   return 0;
 }
 
@@ -190,6 +193,7 @@ int titgpu_set_surface(titgpu_ctx* h, const double* verts, size_t nv, const uint
   c.surface_set = true;
   c.grid_ready = false;
   c.fixed_cache_valid = false;
+  c.dry_pub_valid = false;
   return 0;
 }
 
@@ -214,6 +218,8 @@ int titgpu_upload(titgpu_ctx* h, size_t n_fluid, size_t n_fixed, const char* fie
   if (stride != size_t(w) * 8) { pack_in(host, c.n, w, stride, packed); src = packed.data(); }
   const size_t bytes = c.n * size_t(w) * 8;
   const bool is_state = (f == F_r || f == F_v || f == F_rho || f == F_m);
+  // an upload may change what the wall particles' published fields were computed from (or the fields themselves)
+  if (!(f == F_r && c.fixed_cache_valid) && f != F_dv_dt) c.dry_pub_valid = false;
   if (!is_state) {
     TIT_CUDA_OK(c, cudaMemcpyAsync(c.out[f].p, src, bytes, cudaMemcpyHostToDevice, c.stream));
     if (f == F_dv_dt && c.vt->seed_fmax(c)) return 1;
@@ -230,7 +236,7 @@ int titgpu_upload(titgpu_ctx* h, size_t n_fluid, size_t n_fixed, const char* fie
   if (track_walls) TIT_CUDA_OK(c, cudaMemcpyAsync(&moved, c.scalars.as<int>() + 12, 4, cudaMemcpyDeviceToHost, c.stream));
   TIT_CUDA_OK(c, cudaStreamSynchronize(c.stream));
   c.prof_fold();
-  if (f == F_r && moved) { c.fixed_cache_valid = false; }
+  if (f == F_r && moved) { c.fixed_cache_valid = false; c.dry_pub_valid = false; }
   return 0;
 }
 
