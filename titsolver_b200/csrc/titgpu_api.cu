@@ -130,6 +130,7 @@ int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_
   if (const char* e = std::getenv("TITGPU_TILES")) c.tiles_enabled = e[0] != '0';
   if (const char* e = std::getenv("TITGPU_GRAPHS")) c.graphs_enabled = e[0] != '0';
   if (const char* e = std::getenv("TITGPU_DRY_CACHE")) c.dry_cache_enabled = e[0] != '0';
+  if (const char* e = std::getenv("TITGPU_GROUP_SWEEP")) c.group_sweep = e[0] != '0';
   return 0;
 }
 
