@@ -77,12 +77,26 @@ def test_tile_pass_budgets():
 
 def test_wall_pipeline_budgets():
     res = resources(os.path.join(BUILD, "inst_3_4.o"))
+    # Round-2 sweep of the budgets at C3 (profiles/r2s_wall_variants.txt): the exact sphere / triangle test
+    # needs ~96 registers (at 64 its spill traffic exceeded the global loads: k_wsearch 29.8 -> 21.6 ms per
+    # step), the edge integrals gain more from 64 warps per SM than they lose to 48 bytes of spills
+    # (20.0 -> 17.4 ms), the combine stage is best at 80 registers (10.4 -> 8.7 ms).
     for name, r in pick(res, "k_wevalILi4E").items():
-        assert r["REG"] <= 96 and r["STACK"] == 0, (name, r)  # FP64-heaviest kernel: spill-free
+        assert r["REG"] <= 64 and r["STACK"] <= 64, (name, r)
     for name, r in pick(res, "k_wsearchILi").items():
-        assert r["REG"] <= 64 and r["SHARED"] <= 24 * 1024, (name, r)  # 8 blocks of 4 warps per SM
+        assert r["REG"] <= 96 and r["STACK"] <= 32 and r["SHARED"] <= 24 * 1024, (name, r)  # 5 blocks of 4 warps per SM
     for name, r in pick(res, "k_wcombineILi").items():
-        assert r["REG"] <= 128 and r["STACK"] == 0, (name, r)
+        assert r["REG"] <= 80 and r["STACK"] <= 192, (name, r)  # (the stack of MODE 0 holds the wall sums of the set-up pass only)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_grouped_sweep_budgets(dim):
+    res = resources(os.path.join(BUILD, f"inst_{dim}_4.o"))
+    for name, r in pick(res, f"k_rhs_grpILi{dim}ELi4E").items():
+        assert r["REG"] <= 64 and r["STACK"] <= 64, (name, r)  # same occupancy as k_rhs
+        assert 4 * r["SHARED"] <= 120 * 1024, (name, r)  # 4 lists of 384 16-bit codes per warp
+    for name, r in pick(res, f"k_shift_grpILi{dim}ELi4E").items():
+        assert r["REG"] <= 128, (name, r)
 
 
 def test_streaming_kernels_are_light():

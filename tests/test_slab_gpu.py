@@ -16,8 +16,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_check(*args):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "slab_check.py"), *map(str, args)], capture_output=True, text=True, timeout=900)
+def run_check(*args, env=None):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "slab_check.py"), *map(str, args)], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, **(env or {})))
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-4000:])
     res = json.loads(lines[-1])
@@ -54,3 +55,10 @@ def test_two_slabs_3d_along_z():
 def test_two_slabs_2d_euler_and_verlet():
     for integ in (0, 1):
         run_check("--hub", 2, "--dim", 2, "--n-col", 30, "--steps", 3, "--integrator", integ)
+
+
+def test_slabs_with_the_grouped_candidate_sweep():
+    """The grouped sweep (k_rhs_grp / k_shift_grp, forced on here: it is chosen by size otherwise)
+    skips ghosts as members but reads them as neighbours, like the default traversal."""
+    run_check("--hub", 2, "--dim", 3, "--n-col", 24, "--steps", 2, env={"TITGPU_GROUP_SWEEP": "1"})
+    run_check("--hub", 3, "--dim", 2, "--n-col", 60, "--steps", 4, "--kick", 20.0, "--tol", 1e-7, env={"TITGPU_GROUP_SWEEP": "1"})

@@ -30,7 +30,7 @@ FIELDS = {
 ABI_SYMBOLS = [
     "titgpu_create", "titgpu_destroy", "titgpu_last_error", "titgpu_set_params", "titgpu_set_surface",
     "titgpu_upload", "titgpu_download", "titgpu_initialize", "titgpu_prepare", "titgpu_rhs_only", "titgpu_step",
-    "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_set_tiles", "titgpu_set_graphs", "titgpu_graph_replays", "titgpu_mg_reserve", "titgpu_mg_counts",
+    "titgpu_set_outputs", "titgpu_set_lists", "titgpu_list_redos", "titgpu_set_tiles", "titgpu_set_group_sweep", "titgpu_set_graphs", "titgpu_graph_replays", "titgpu_mg_reserve", "titgpu_mg_counts",
     "titgpu_mg_set_slab", "titgpu_mg_set_halo_pair", "titgpu_mg_set_gids", "titgpu_mg_attach_comm", "titgpu_mg_nccl_unique_id", "titgpu_mg_attach_nccl", "titgpu_mg_hub_create", "titgpu_mg_hub_destroy",
     "titgpu_mg_attach_hub", "titgpu_mg_detach", "titgpu_mg_download_owned", "titgpu_mg_upload_owned", "titgpu_mg_stats",
     "titgpu_neighbors", "titgpu_face_neighbors", "titgpu_synchronize", "titgpu_launch_count", "titgpu_stream", "titgpu_version",
@@ -71,6 +71,7 @@ def load_library() -> C.CDLL:
     lib.titgpu_set_outputs.argtypes = [vp, C.c_int]
     lib.titgpu_set_lists.argtypes = [vp, C.c_int]
     lib.titgpu_set_tiles.argtypes = [vp, C.c_int]
+    lib.titgpu_set_group_sweep.argtypes = [vp, C.c_int]
     lib.titgpu_set_graphs.argtypes = [vp, C.c_int]
     lib.titgpu_graph_replays.argtypes = [vp]
     lib.titgpu_graph_replays.restype = C.c_ulonglong
@@ -231,6 +232,10 @@ class Solver:
     @property
     def graph_replays(self):
         return int(self.lib.titgpu_graph_replays(self.h))
+
+    def set_group_sweep(self, mode):
+        """Grouped candidate sweep of the kernel-sum passes: -1 / None = by particle count (default), 0 = never, 1 = always (titgpu_set_group_sweep). Bit-identical results either way."""
+        self._ck(self.lib.titgpu_set_group_sweep(self.h, -1 if mode is None else int(mode)), "titgpu_set_group_sweep")
 
     def set_tiles(self, on):
         """Shared-memory-staged kernel-sum pass on / off (titgpu_set_tiles; 3-D, radius-2h kernels)."""

@@ -128,7 +128,7 @@ struct Ctx {
     unsigned long long launches;
     cudaGraphExec_t exec;
   };
-  bool group_sweep = false;    // TITGPU_GROUP_SWEEP=1: k_rhs_grp (one candidate sweep per 4 consecutive particles) instead of k_rhs
+  int group_sweep = -1;        // grouped candidate sweep (k_rhs_grp / k_shift_grp): -1 = by size (n >= kGroupMinN), 0 = never, 1 = always (titgpu_set_group_sweep / TITGPU_GROUP_SWEEP)
   bool graphs_enabled = true;  // TITGPU_GRAPHS=0 / titgpu_set_graphs
   std::vector<StepGraph> graphs;
   unsigned long long graph_replays = 0;

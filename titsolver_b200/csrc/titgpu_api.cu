@@ -130,7 +130,7 @@ int titgpu_create(titgpu_ctx** out, int device, int dim, int kernel_id, int eos_
   if (const char* e = std::getenv("TITGPU_TILES")) c.tiles_enabled = e[0] != '0';
   if (const char* e = std::getenv("TITGPU_GRAPHS")) c.graphs_enabled = e[0] != '0';
   if (const char* e = std::getenv("TITGPU_DRY_CACHE")) c.dry_cache_enabled = e[0] != '0';
-  if (const char* e = std::getenv("TITGPU_GROUP_SWEEP")) c.group_sweep = e[0] != '0';
+  if (const char* e = std::getenv("TITGPU_GROUP_SWEEP")) c.group_sweep = e[0] == 'a' ? -1 : e[0] != '0';
   return 0;
 }
 
@@ -327,6 +327,11 @@ int titgpu_set_graphs(titgpu_ctx* h, int on) {
   return 0;
 }
 unsigned long long titgpu_graph_replays(const titgpu_ctx* h) { return h ? h->c.graph_replays : 0; }
+int titgpu_set_group_sweep(titgpu_ctx* h, int mode) {
+  if (!h) return 1;
+  h->c.group_sweep = mode < 0 ? -1 : mode != 0;
+  return 0;
+}
 int titgpu_set_tiles(titgpu_ctx* h, int on) {
   if (!h) return 1;
   h->c.tiles_enabled = on != 0;

@@ -14,8 +14,8 @@ from titsolver_b200 import cases
 
 
 def run(case, grouped, steps):
-    os.environ["TITGPU_GROUP_SWEEP"] = "1" if grouped else "0"
     g = tb.Solver(case.dim)
+    g.set_group_sweep(1 if grouped else 0)
     g.set_graphs(False)
     tb.load_case(g, case)
     g.initialize()
