@@ -288,3 +288,32 @@ def test_shared_memory_staged_pass_equals_the_gather_traversal(oracle, lattice):
         c.step(2)
         for f in STATE:
             assert rel_err(res[0][f], c.download(f)) <= 1e-10, f
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_size_selected_grouped_sweep_equals_the_gather_traversal_at_scale(dim):
+    """Above 2^19 particles the kernel-sum passes switch to the grouped candidate sweep by
+    themselves (titgpu_set_group_sweep, default -1). Everything the parity tests establish on
+    small cases carries over only if that path is the same function: a case large enough to
+    select it (3-D lattice n_col = 60, 0.68 M particles; 2-D n_col = 540, 0.59 M, whole steps
+    replayed as CUDA graphs) must match the forced gather traversal bit for bit."""
+    case = cases.dam_break_2d(540) if dim == 2 else cases.dam_break_3d(60)
+    assert case.n >= 1 << 19
+    res = []
+    for mode in (None, 0):
+        g = tb.Solver(dim)
+        g.set_group_sweep(mode)
+        tb.load_case(g, case)
+        g.initialize()
+        g.profile(True)
+        g.step(1)
+        names = set(g.profile_read())
+        g.profile(False)
+        g.step(7)
+        res.append({f: g.download(f) for f in STATE + ("N", "phi", "dv_dt", "drho_dt", "grad_v", "dr")})
+        assert any("k_rhs_grp" in k for k in names) == (mode is None), names
+        assert any("k_shift_grp" in k for k in names) == (mode is None), names
+        if dim == 2:
+            assert g.graph_replays > 0
+    for f in res[0]:
+        assert np.array_equal(res[0][f], res[1][f], equal_nan=True), f
