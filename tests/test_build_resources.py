@@ -60,7 +60,7 @@ def test_pair_pass_budgets(dim, kid):
         # local-memory traffic in the pair loop (profiles/r02f: 17 M local vs 518 M global load wavefronts).
         assert r["STACK"] <= 640, (name, r)
     for name, r in pick(res, f"k_near_surfaceILi{dim}E").items():
-        assert r["REG"] <= 64 and r["STACK"] == 0, (name, r)
+        assert r["REG"] <= 64 and r["STACK"] <= 16, (name, r)
 
 
 def test_tile_pass_budgets():
