@@ -82,28 +82,30 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_pipes(dim):
-    """Pipe utilisation of k_rhs from the committed `ncu --set full` capture (profiles/ncu_traffic.json):
-    FP64 / FP32 (FMA) pipe and L1 data-pipe busy %, issue-slot utilisation."""
+def ncu_record(dim, kernel):
+    """The committed `ncu --set full` capture of the kernel-sum pass that ran (profiles/ncu_traffic.json,
+    written by tools/ncu_traffic_update.py): the grouped sweep `k_rhs_grp` on large particle counts, the
+    gather traversal `k_rhs` otherwise."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
-            rec = json.load(f).get("k_rhs", {}).get(f"{dim}d")
+            db = json.load(f)
     except (OSError, ValueError):
         return None
+    key = "k_rhs_grp" if kernel and "k_rhs_grp" in kernel else "k_rhs"
+    return db.get(key, {}).get(f"{dim}d")
+
+
+def ncu_pipes(dim, kernel=None):
+    """Pipe utilisation of that launch: FP64 / FP32 (FMA) pipe and L1 data-pipe busy %, issue-slot utilisation."""
+    rec = ncu_record(dim, kernel)
     return rec.get("pipes") if rec else None
 
 
-def ncu_traffic(dim, n):
-    """DRAM bytes (read + write) of one k_rhs launch over n particles, from the committed
-    `ncu --set full` capture (profiles/ncu_traffic.json: bytes per particle measured at the
-    capture's size, scaled to this launch); None when no capture exists for this dimension."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    try:
-        with open(path) as f:
-            rec = json.load(f).get("k_rhs", {}).get(f"{dim}d")
-    except (OSError, ValueError):
-        return None, None
+def ncu_traffic(dim, n, kernel=None):
+    """DRAM bytes (read + write) of one launch over n particles (bytes per particle measured at the
+    capture's size, scaled to this launch); None when no capture exists for this kernel and dimension."""
+    rec = ncu_record(dim, kernel)
     if not rec:
         return None, None
     return rec["bytes_per_particle"] * n, rec["source"]
@@ -520,7 +522,7 @@ def run_ours(args, rank, local_rank, world):
         avg_s = tot / cnt * 1e-3
         ach = alg_bytes_rhs(dim) * n / avg_s / 1e9
         flops = alg_flops_rhs(dim) * (n_fluid / world) / avg_s / 1e12
-        traffic, traffic_src = ncu_traffic(dim, n)
+        traffic, traffic_src = ncu_traffic(dim, n, rhs_name)
         roof = {
             # The kernel-sum pass is bound by the FP64 pipe / instruction issue, not by HBM: its
             # algorithmic intensity is ~180 flop per compulsory byte. The HBM
@@ -532,7 +534,7 @@ def run_ours(args, rank, local_rank, world):
             "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read + write)", "traffic_source": traffic_src,
             "hbm": {"achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "alg_bytes_per_particle": alg_bytes_rhs(dim), "peak_source": peak_src,
                     "dram_frac": (traffic / avg_s / 1e9 / hbm_peak) if traffic else None},
-            "pipes": ncu_pipes(dim),
+            "pipes": ncu_pipes(dim, rhs_name),
             "step": {"alg_bytes_per_update": alg_bytes_step(dim), "achieved_gbs": alg_bytes_step(dim) * value / world / 1e9,
                      "frac": alg_bytes_step(dim) * value / world / 1e9 / hbm_peak},
         }
