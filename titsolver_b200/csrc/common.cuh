@@ -173,6 +173,7 @@ struct GridDesc {
   double cinv;  // 1 / cell size
   int nc[3];
   int ncells;
+  int tyl;  // 3-D search grid: log2 of the tile width along y of the cell order (0 = plain row-major), see col_base
 };
 
 struct Params {

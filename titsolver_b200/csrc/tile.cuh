@@ -92,7 +92,7 @@ static __global__ void k_tile_list(const unsigned char* __restrict__ cell_fluid,
       for (int dy = 0; dy < 2 && !take; ++dy) {
         const int cx = 2 * tx + dx, cy = 2 * ty + dy;
         if (cx < g.nc[0] && cy < g.nc[1]) {
-          const int base = (cx * g.nc[1] + cy) * g.nc[2];
+          const int base = col_base<3>(g, cx, cy);
           for (int z = z0; z < z1; ++z) take = take || cell_fluid[base + z] != 0;
         }
       }
@@ -118,7 +118,7 @@ __device__ __forceinline__ void tile_prefetch(const Dev<3>& S, TileSmem& T, int 
     const int cx = 2 * tx - 2 + rc / 6, cy = 2 * ty - 2 + rc % 6;
     if (cx >= 0 && cx < g.nc[0] && cy >= 0 && cy < g.nc[1]) {
       const int cz = min(max(2 * tz - 2 + zz, 0), g.nc[2]);  // == nc[2]: the end of the column
-      const int* src = S.cell_start + ((cx * g.nc[1] + cy) * g.nc[2] + cz);
+      const int* src = S.cell_start + (col_base<3>(g, cx, cy) + cz);
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&T.pre[rc][zz])), "l"(src) : "memory");
     } else {
       T.pre[rc][zz] = 0;  // a column outside the grid: empty
