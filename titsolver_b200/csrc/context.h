@@ -139,7 +139,6 @@ struct Ctx {
 
   // Hash / sort scratch.
   DBuf cell_id, slot, tmp_perm, perm, cell_cnt, cell_start, cub_tmp, cell_fs, cell_fluid;
-  DBuf cell_fs_near, cell_fluid_near, cell_tmp;  // the two flags dilated by KC_ cells (k_dilate_axis) + scratch
 
   // Static boundary.
   DBuf frames, fcell_start, fcell_faces, face_cells, fflag, ftwin, fterm, fgeom, favg;

@@ -148,7 +148,7 @@ __global__ void k_mg_scatter_nphi(const double4* __restrict__ src, const int* __
     Pack<D>::pos(A, a, r, rho_unused);
     int ci[D];
     cell_coords<D>(g, r, ci);
-    cell_fs[cell_flat<D>(g, ci)] = 1;
+    thread_mark_cell_block<D>(g, ci, cell_fs);  // as the owner's warp does for its own particles (shift_finish)
   }
 }
 
