@@ -62,3 +62,12 @@ def test_slabs_with_the_grouped_candidate_sweep():
     skips ghosts as members but reads them as neighbours, like the default traversal."""
     run_check("--hub", 2, "--dim", 3, "--n-col", 24, "--steps", 2, env={"TITGPU_GROUP_SWEEP": "1"})
     run_check("--hub", 3, "--dim", 2, "--n-col", 60, "--steps", 4, "--kick", 20.0, "--tol", 1e-7, env={"TITGPU_GROUP_SWEEP": "1"})
+
+
+def test_slabs_with_the_tiled_cell_order():
+    """The y-tiled cell order (chosen by the grid on large cross-sections, forced to tiles of 4 cells here)
+    under a slab decomposition, with the grouped sweep on: ghosts, migration and the exchanges do not
+    depend on the order of the sorted arrays."""
+    env = {"TITGPU_YTILE_LOG": "2", "TITGPU_GROUP_SWEEP": "1"}
+    run_check("--hub", 2, "--dim", 3, "--n-col", 24, "--steps", 3, env=env)
+    run_check("--hub", 3, "--dim", 3, "--n-col", 20, "--steps", 2, "--lattice", env=env)
