@@ -474,3 +474,40 @@ def test_grouped_candidate_sweep_is_bit_identical(dim, kernel_id, eos_id):
         res.append(out)
     for f in res[0]:
         assert np.array_equal(res[0][f], res[1][f], equal_nan=True), f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 3])
+def test_grouped_sweep_falls_back_when_a_hit_list_overflows(oracle, dim):
+    """A smoothing length far above the lattice spacing gives every particle more neighbours than a
+    member's list of the grouped sweep holds (384; here ~500 in 2-D, ~1100 in 3-D): the group must
+    leave the sweep half-way and take the gather traversal, which in turn drains its own list
+    (512 entries) in the middle of the sweep. Same results bit for bit as with the grouped sweep off,
+    and the oracle agrees on the right-hand sides."""
+    import dataclasses
+
+    base = cases.dam_break_2d(20) if dim == 2 else cases.dam_break_3d(8, wall_ratio=0.93, jitter=0.1)
+    case = dataclasses.replace(base, h=base.h * (3.2 if dim == 2 else 1.6))
+    res = []
+    for mode in (1, 0):
+        g = tb.Solver(dim)
+        g.set_graphs(False)
+        g.set_group_sweep(mode)
+        tb.load_case(g, case)
+        g.initialize()
+        g.rhs_only()
+        out = {"rhs_" + f: g.download(f) for f in ("drho_dt", "dv_dt")}
+        g.step(2)
+        out.update({f: g.download(f) for f in STEP_FIELDS + ("N", "phi", "grad_v")})
+        res.append(out)
+    for f in res[0]:
+        assert np.array_equal(res[0][f], res[1][f], equal_nan=True), f
+    off, _ = g.neighbors()
+    assert np.diff(off)[: case.n_fluid].max() > 384
+    c = oracle.OracleSolver(dim, 4, 0, 3)
+    oracle.load_case(c, case)
+    c.initialize()
+    c.rhs_only()
+    nf = case.n_fluid
+    for f in ("drho_dt", "dv_dt"):
+        assert rel_err(res[0]["rhs_" + f][:nf], c.download(f)[:nf]) < 1e-9, f
