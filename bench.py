@@ -191,6 +191,7 @@ class CpuReference:
 
         def make(case):
             s = oracle_lib.OracleSolver(dim, fast=True)
+            s.set_symmetric(os.environ.get("BENCH_CPU_GATHER") is None)  # the reference's loop structure: every pair once, both particles updated
             s.lib.orc_set_num_threads(self.threads)  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
             oracle_lib.load_case(s, case)
             s.initialize()
@@ -254,7 +255,7 @@ def cpu_baseline_sample(dim, n_col, budget_s=30.0, tank_z=1.0):
             break
     return {"value": ref.n * steps / est, "unit": UNIT, "cores": ref.cores, "kind": "port", "seconds_per_step": est / steps,
             "phase_seconds_per_step": {k: round(v / steps, 4) for k, v in ref.phase_s.items()},
-            "sample": f"{steps} SSPRK3 steps; {ref.sample}; oracle/liboracle_fast.so (-O3, OpenMP, gather-form pair sums)"}
+            "sample": f"{steps} SSPRK3 steps; {ref.sample}; oracle/liboracle_fast.so (-O3, OpenMP, symmetric block-coloured pair sums as in particle_mesh.hpp:165-241)"}
 
 
 def bench_config(w, args, dim, n_col, world, n_fluid, n_fixed, strong_main):
@@ -301,7 +302,7 @@ def run_reference(args, rank, world):
         "config": bench_config(w, args, dim, n_col, world, ref.n_fluid, ref.n_fixed, strong_main),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": ref.cores, "kind": "port", "seconds_per_step": est / args.steps, "measured_wall_seconds": wall,
                          "phase_seconds_per_step": {k: round(v / args.steps, 4) for k, v in ref.phase_s.items()},
-                         "sample": f"{args.steps} SSPRK3 steps; {ref.sample}; oracle/liboracle_fast.so (-O3, OpenMP, gather-form pair sums)"},
+                         "sample": f"{args.steps} SSPRK3 steps; {ref.sample}; oracle/liboracle_fast.so (-O3, OpenMP, symmetric block-coloured pair sums as in particle_mesh.hpp:165-241)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference (OpenMP, all host cores); the reference itself (C++26, oneTBB) cannot be built in this image",
     }

@@ -68,6 +68,9 @@ int orc_set_params(void* h, double g, double mu, double cs0, double rho0, double
   s->prm.search_hint = search_hint; s->prm.face_hint = face_hint;
   return 0;
 }
+// 1: the pair sums run over unordered pairs and update both particles (the reference's own loop
+// structure, block-coloured: SimBase Sim::for_each_pair); 0 (default): gather form with a fixed order.
+int orc_set_symmetric(void* h, int on) { static_cast<SimBase*>(h)->prm.symmetric = on != 0; return 0; }
 int orc_set_surface(void* h, const double* v, size_t nv, const uint64_t* f, size_t nf, const double* cv, size_t ncv, const uint64_t* cf, size_t ncf) {
   return static_cast<SimBase*>(h)->set_surface(v, nv, f, nf, cv, ncv, cf, ncf);
 }

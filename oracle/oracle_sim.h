@@ -37,6 +37,7 @@ struct Params {
   double search_hint = 0.0, face_hint = 0.0;
   int eos = 0;         // 0 Tait, 1 linear Tait
   int integrator = 3;  // 0 symplectic Euler, 1 velocity Verlet, 2 SSPRK2, 3 SSPRK3
+  int symmetric = 0;   // 1: pair sums over unordered pairs, both particles updated per pair (see for_each_pair)
 };
 
 struct SimBase {
@@ -366,8 +367,149 @@ struct Sim final : SimBase {
     return dt;
   }
 
+  // ---- symmetric pair loops ----
+  // The reference evaluates every unordered pair ONCE and updates both particles
+  // (fluid_equations.hpp:249-259, 293-304, 351-365), made race-free by a two-level
+  // partition of the particles into blocks (particle_mesh.hpp:165-241): pairs inside a
+  // block run in parallel over the blocks, the pairs between blocks in a later pass. The
+  // same scheme with slabs along x at least one support radius thick: a pair joins
+  // particles of one slab or of two adjacent slabs, so three passes cover every pair
+  // exactly once without two threads touching one particle - slab-internal pairs (all
+  // slabs in parallel), pairs (i, i + 1) for even i, then for odd i. Used by the CPU
+  // baseline of bench.py (prm.symmetric = 1); the parity oracle keeps the gather form,
+  // whose sums have a fixed order. tests/test_oracle_physics.py checks that the two agree.
+  std::vector<std::uint32_t> blk_of, blk_off, blk_items;
+  void build_blocks() {
+    const std::size_t nn = n();
+    double lo = 1e300, hi = -1e300;
+    for (std::size_t a = 0; a < nn; ++a) { lo = std::min(lo, r[a][0]); hi = std::max(hi, r[a][0]); }
+    const double width = radius() * 1.0001;
+    const std::size_t nb_ = std::size_t(std::max(1.0, std::floor((hi - lo) / width))) + 1;
+    blk_of.assign(nn, 0);
+    blk_off.assign(nb_ + 1, 0);
+    for (std::size_t a = 0; a < nn; ++a) {
+      blk_of[a] = std::uint32_t(std::min<double>(double(nb_ - 1), std::floor((r[a][0] - lo) / width)));
+      blk_off[blk_of[a] + 1]++;
+    }
+    for (std::size_t i = 0; i < nb_; ++i) blk_off[i + 1] += blk_off[i];
+    blk_items.resize(nn);
+    std::vector<std::uint32_t> pos(blk_off.begin(), blk_off.end() - 1);
+    for (std::size_t a = 0; a < nn; ++a) blk_items[pos[blk_of[a]]++] = std::uint32_t(a);
+  }
+  // fn(a, b) once per unordered pair of distinct neighbours.
+  template<class F> void for_each_pair(F&& fn) {
+    build_blocks();
+    const long nblk = long(blk_off.size()) - 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long i = 0; i < nblk; ++i)
+      for (std::uint32_t k = blk_off[i]; k < blk_off[i + 1]; ++k) {
+        const std::size_t a = blk_items[k];
+        for (std::uint32_t j = nb_off[a]; j < nb_off[a + 1]; ++j) {
+          const std::size_t b = nb[j];
+          if (b > a && blk_of[b] == std::uint32_t(i)) fn(a, b);
+        }
+      }
+    for (long parity = 0; parity < 2; ++parity) {
+#pragma omp parallel for schedule(dynamic, 1)
+      for (long i = parity; i < nblk - 1; i += 2)
+        for (std::uint32_t k = blk_off[i]; k < blk_off[i + 1]; ++k) {
+          const std::size_t a = blk_items[k];
+          for (std::uint32_t j = nb_off[a]; j < nb_off[a + 1]; ++j) {
+            const std::size_t b = nb[j];
+            if (blk_of[b] == std::uint32_t(i + 1)) fn(a, b);
+          }
+        }
+    }
+  }
+  void compute_continuity_symmetric() {
+    const std::size_t nn = n();
+    const double h = prm.h;
+#pragma omp parallel for schedule(static)
+    for (std::size_t a = 0; a < nn; ++a) cs[a] = eos_cs(rho[a]);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (std::size_t a = 0; a < nf; ++a) {
+      double acc = 0.0;
+      for (std::uint32_t i = fc_off[a]; i < fc_off[a + 1]; ++i) {
+        const std::uint32_t s = fc[i];
+        const V gg = K::flux(domain.face(s), r[a], h);
+        acc -= favg(rho, s) * dot(v[a] - favg(v, s), gg) / gamma[a];
+      }
+      drho_dt[a] = acc;
+    }
+    for_each_pair([&](std::size_t a, std::size_t b) {
+      const V r_ab = r[a] - r[b];
+      const V gW = K::template grad<D>(r_ab, h);
+      const double cs_ab = std::max(cs[a], cs[b]);
+      const V Psi = (cs_ab * (rho[a] - rho[b]) * r_ab) / norm(r_ab);  // Psi_ab = Psi_ba
+      const V v_ab = v[a] - v[b];
+      if (a < nf) drho_dt[a] += m[b] / gamma[a] * dot(v_ab + Psi / rho[b], gW);
+      if (b < nf) drho_dt[b] += m[a] / gamma[b] * dot(v_ab - Psi / rho[a], gW);  // (v_ba + Psi / rho_a) . grad W_ba
+    });
+  }
+  void compute_momentum_symmetric() {
+    const std::size_t nn = n();
+    const double h = prm.h;
+#pragma omp parallel for schedule(static)
+    for (std::size_t a = 0; a < nn; ++a) p[a] = eos_p(rho[a]);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (std::size_t a = 0; a < nf; ++a) {
+      V acc{};
+      acc[1] = -prm.g;
+      for (std::uint32_t i = fc_off[a]; i < fc_off[a + 1]; ++i) {
+        const std::uint32_t s = fc[i];
+        const V gg = K::flux(domain.face(s), r[a], h);
+        const double rho_s = favg(rho, s), p_s = favg(p, s);
+        const double P_as = rho_s * (p[a] / pow2(rho[a]) + p_s / pow2(rho_s));
+        const V n_s = normalize(gg);
+        const V v_as = v[a] - favg(v, s);
+        const V t_as = normalize(v_as - dot(v_as, n_s) * n_s);
+        const double dr_as = std::max(h / 2.0, dot(r[a] - favg(r, s), n_s));
+        const V Pi_as = (2.0 * prm.mu / (rho[a] * dr_as) * dot(v_as, t_as)) * t_as;
+        acc += (P_as * gg - Pi_as * norm(gg)) / gamma[a];
+      }
+      dv_dt[a] = acc;
+    }
+    for_each_pair([&](std::size_t a, std::size_t b) {
+      const V r_ab = r[a] - r[b];
+      const V gW = K::template grad<D>(r_ab, h);
+      const double P_ab = p[a] / pow2(rho[a]) + p[b] / pow2(rho[b]);
+      const double Pi_ab = 2.0 * prm.mu * dot(v[a] - v[b], r_ab) / (rho[a] * rho[b] * norm2(r_ab));
+      if (a < nf) dv_dt[a] += (m[b] / gamma[a] * (Pi_ab - P_ab)) * gW;
+      if (b < nf) dv_dt[b] -= (m[a] / gamma[b] * (Pi_ab - P_ab)) * gW;
+    });
+  }
+  // The sums of apply_shifts over unordered pairs: raw Na -> dr, La -> L, gv -> grad_v, gr -> grad_rho.
+  void shift_sums_symmetric() {
+    const std::size_t nn = n();
+    const double h = prm.h;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (std::size_t a = 0; a < nn; ++a) {
+      V Na{}, gr{};
+      M La{}, gv{};
+      for (std::uint32_t i = fc_off[a]; i < fc_off[a + 1]; ++i) {
+        const std::uint32_t s = fc[i];
+        const V gg = K::flux(domain.face(s), r[a], h);
+        Na -= gg / gamma[a];
+        La -= outer(favg(r, s) - r[a], gg) / gamma[a];
+        gv -= outer(favg(v, s) - v[a], gg) / gamma[a];
+        gr -= ((favg(rho, s) - rho[a]) * gg) / gamma[a];
+      }
+      dr[a] = Na; L[a] = La; grad_v[a] = gv; grad_rho[a] = gr;
+    }
+    for_each_pair([&](std::size_t a, std::size_t b) {
+      const V gW = K::template grad<D>(r[a] - r[b], h);
+      const M o_r = outer(r[b] - r[a], gW), o_v = outer(v[b] - v[a], gW);
+      const V g_rho = (rho[b] - rho[a]) * gW;
+      const double ca = m[b] / rho[b] / gamma[a], cb = m[a] / rho[a] / gamma[b];
+      dr[a] += ca * gW; L[a] += ca * o_r; grad_v[a] += ca * o_v; grad_rho[a] += ca * g_rho;
+      // b's terms: grad W_ba = -grad W_ab, r_a - r_b = -(r_b - r_a), ...: the outer products and g_rho keep their sign
+      dr[b] -= cb * gW; L[b] += cb * o_r; grad_v[b] += cb * o_v; grad_rho[b] += cb * g_rho;
+    });
+  }
+
   // ---- fluid_equations.hpp:232-260 ----
   void compute_continuity() {
+    if (prm.symmetric) return compute_continuity_symmetric();
     const std::size_t nn = n();
     const double h = prm.h;
 #pragma omp parallel for schedule(static)
@@ -395,6 +537,7 @@ struct Sim final : SimBase {
 
   // ---- fluid_equations.hpp:267-305 ----
   void compute_momentum() {
+    if (prm.symmetric) return compute_momentum_symmetric();
     const std::size_t nn = n();
     const double h = prm.h;
 #pragma omp parallel for schedule(static)
@@ -433,11 +576,14 @@ struct Sim final : SimBase {
     const std::size_t nn = n();
     const double h = prm.h;
     const double rad = radius();
+    const bool sym = prm.symmetric != 0;
+    if (sym) shift_sums_symmetric();
 #pragma omp parallel for schedule(dynamic, 256)
     for (std::size_t a = 0; a < nn; ++a) {
       V Na{}, gr{};
       M La{}, gv{};
-      for (std::uint32_t i = fc_off[a]; i < fc_off[a + 1]; ++i) {
+      if (sym) { Na = dr[a]; La = L[a]; gv = grad_v[a]; gr = grad_rho[a]; }
+      for (std::uint32_t i = fc_off[a]; !sym && i < fc_off[a + 1]; ++i) {
         const std::uint32_t s = fc[i];
         const V gg = K::flux(domain.face(s), r[a], h);
         Na -= gg / gamma[a];
@@ -445,7 +591,7 @@ struct Sim final : SimBase {
         gv -= outer(favg(v, s) - v[a], gg) / gamma[a];
         gr -= ((favg(rho, s) - rho[a]) * gg) / gamma[a];
       }
-      for (std::uint32_t i = nb_off[a]; i < nb_off[a + 1]; ++i) {
+      for (std::uint32_t i = nb_off[a]; !sym && i < nb_off[a + 1]; ++i) {
         const std::size_t b = nb[i];
         if (b == a) continue;
         const double V_b = m[b] / rho[b];

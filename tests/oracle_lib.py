@@ -47,6 +47,7 @@ def load(fast: bool = False) -> C.CDLL:
     lib.orc_download.argtypes = [vp, C.c_char_p, dp]
     lib.orc_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.orc_phase_times.argtypes = [vp, dp, C.c_int]
+    lib.orc_set_symmetric.argtypes = [vp, C.c_int]
     for f in ("orc_initialize", "orc_prepare", "orc_rhs_only", "orc_post_only"):
         getattr(lib, f).argtypes = [vp]
     lib.orc_step.argtypes = [vp, C.c_int, dp]
@@ -165,6 +166,11 @@ class OracleSolver:
         return dict(zip(self.STAT_NAMES, [int(x) for x in a]))
 
     PHASE_NAMES = ("search", "compute_gamma", "setup_boundary", "continuity_momentum", "update_lincomb_dt", "apply_shifts", "free_surface_correction")
+
+    def set_symmetric(self, on=True):
+        """Pair sums over unordered pairs, both particles updated per pair, block-coloured (the reference's
+        loop structure; CPU baseline of bench.py). Default off: gather form with a fixed order of every sum."""
+        self.lib.orc_set_symmetric(self.h, int(bool(on)))
 
     def phase_times(self, reset=True):
         """Seconds per phase accumulated since the last reset (oracle_sim.h, SimBase::phase_s)."""
