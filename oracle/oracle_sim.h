@@ -13,15 +13,19 @@
 //   geom/face_search/grid_face_search.hpp:43-112 face cell list
 //
 // Parity status: the kernel / geometry layers are pinned by the reference's
-// known-answer tests (tests/test_oracle_*.py). FluidEquations, ParticleMesh
-// and the integrators have NO reference unit test and the reference cannot be
-// built here (C++26, GCC 16): for those this oracle is "parity unpinned" beyond
-// physical sanity checks.
+// known-answer tests (tests/test_oracle_kernels.py, test_oracle_geometry.py).
+// FluidEquations, ParticleMesh and the integrators have NO reference unit test
+// and the reference cannot be built here (C++26, GCC 16): they are pinned by an
+// independent numpy transcription of the reference's lambdas in their original
+// symmetric scatter form plus known physical answers (tests/test_oracle_physics.py;
+// DESIGN.md section 5). The 3-D dam break has no counterpart in the reference.
 //
 // The pair loops of the reference are symmetric (update a and b per unordered
 // pair); the gather form used here is algebraically and bitwise term-identical
 // (Psi_ab = Psi_ba, Pi_ab = Pi_ba, P_ab = P_ba, grad W_ab = -grad W_ba) and
-// sums each particle's terms in ascending neighbour index.
+// sums each particle's terms in ascending neighbour index. prm.symmetric = 1
+// switches the pair sums to the reference's own structure (for_each_pair): the
+// CPU baseline of bench.py uses that, the parity tests never do.
 #pragma once
 
 #include <chrono>
